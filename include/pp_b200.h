@@ -1,0 +1,195 @@
+/*
+ * pp_b200.h -- C ABI of libpp_b200.so: the B200 (sm_100a) implementation of the
+ * PointPillars pre/post-processing hot path of michalp0lak/ObjectDetection_3D.
+ *
+ * Every entry point is what a binding of the reference's ops layer would call; the
+ * reference interface each one replaces is cited as file:line (paths inside the
+ * reference checkout).  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers unless the name ends in _host.
+ *  - The caller owns every buffer (outputs and workspace); the library never allocates
+ *    or retains device memory in the device-pointer entry points.  Workspace sizes come
+ *    from the matching *_workspace_bytes function; workspaces need no initialisation.
+ *  - Work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises
+ *    unless stated.  Data-dependent sizes (pillar count, keep count) are returned through
+ *    device scalars so that the caller decides when to synchronise.
+ *  - Return value: 0 on success, negative PP_ERR_* otherwise; pp_last_error() returns a
+ *    thread-local message.  No exception crosses the boundary.  The Python mirror turns
+ *    PP_ERR_INVALID into ValueError/AssertionError like the reference's own checks
+ *    (ops/ops_torch.py:555-562, 643-646).
+ */
+#ifndef PP_B200_H
+#define PP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_OK 0
+#define PP_ERR_INVALID (-1)   /* bad argument */
+#define PP_ERR_CUDA (-2)      /* launch / runtime failure, see pp_last_error() */
+#define PP_ERR_WORKSPACE (-3) /* workspace too small */
+
+typedef void *pp_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define PP_API __attribute__((visibility("default")))
+#else
+#define PP_API
+#endif
+
+PP_API int pp_version(void);
+PP_API const char *pp_last_error(void);
+/* number of kernels this library has launched in this process (for gpu_launches accounting) */
+PP_API int64_t pp_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1 -- hard voxelization.
+ * Replaces ops/ops_numba.py:109-168 points_to_voxel and its two kernels (:171-240 given /
+ * shuffled order, :242-308 reflectance pre-order), called from VoxelGenerator.generate (:56-60),
+ * CustomVoxelGenerator.generate (:95-99) and PointPillarsVoxelization.forward
+ * (model/PointPillars.py:330-354).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    double range[6];     /* coors_range xyzxyz, exactly converted to double                 */
+    double vsize[3];     /* voxel_size, exactly converted to double                         */
+    int32_t range_is_f64; /* numba promotion: (p - range) is done in f64 iff range is f64   */
+    int32_t vsize_is_f64; /* the division is f64 iff range or voxel_size is f64             */
+    int32_t grid[3];     /* np.round((range[3:]-range[:3])/vsize) as in ops_numba.py:144-145 */
+    int32_t max_points;  /* P, points kept per pillar                                        */
+    int32_t max_voxels;  /* pillar cap; the (cap+1)-th new pillar BREAKS the pass (:223,:291) */
+    int32_t num_feats;   /* C, floats per point (>= 3; >= 4 for PP_ORDER_REFLECTANCE_DESC)    */
+} pp_voxel_cfg;
+
+enum {
+    PP_ORDER_GIVEN = 0,            /* process points in array order (replay of the shuffled order) */
+    PP_ORDER_REFLECTANCE_DESC = 1, /* points[:,3] descending; ties: lower original index first     */
+    PP_ORDER_PERM = 2              /* caller-supplied permutation: position p reads points[perm[p]] */
+};
+
+/* rows the caller must allocate for voxels/coors/num_points: min(max_voxels, N, cells) */
+PP_API int64_t pp_voxelize_max_rows(int64_t n_points, const pp_voxel_cfg *cfg);
+PP_API size_t pp_voxelize_workspace_bytes(int64_t n_points, const pp_voxel_cfg *cfg, int order);
+
+/*
+ * points     (N, C) f32
+ * perm       (N) int32, only for PP_ORDER_PERM (else NULL)
+ * voxels     (rows, P, C) f32   rows < *voxel_num are fully written (zero padded)
+ * coors      (rows, 3) int32    xyz cell index, like the numpy return (:164)
+ * num_points (rows) int32
+ * voxel_num  device int32 scalar = number of pillars (the reference's slice bound, :164-166)
+ * pillar_map optional (may be NULL): (gx*gy*gz) int32 written with the pillar id of every
+ *            occupied cell and -1 elsewhere (cell = (z*gy + y)*gx + x, i.e. the (D,H,W) order of
+ *            the BEV canvas), for the fused scatter.
+ */
+PP_API int pp_voxelize(const float *points, int64_t n_points, const pp_voxel_cfg *cfg, int order,
+                const int32_t *perm, float *voxels, int32_t *coors, int32_t *num_points,
+                int32_t *voxel_num, int32_t *pillar_map, void *workspace, size_t workspace_bytes,
+                pp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 2 -- pillar decoration, PFN and dense scatter.
+ * ---------------------------------------------------------------------------------------- */
+enum {
+    PP_COORS_XYZ_I32 = 0,  /* (M,3) int32 x,y,z  (pp_voxelize output) + a single batch index */
+    PP_COORS_BZYX_I32 = 1, /* (M,4) int32 b,z,y,x (SparseMiddleExtractor after .int())        */
+    PP_COORS_BZYX_I64 = 2  /* (M,4) int64 b,z,y,x (PointPillars.voxelize output)              */
+};
+enum { PP_NUM_I32 = 0, PP_NUM_I64 = 1 };
+
+/*
+ * Decoration only.  Replaces PillarFeatureNet.forward up to the padding mask,
+ * model/PointPillars.py:490-521 (+ get_paddings_indicator, model/utils.py:442-458).
+ * out (M, P, C+5) = [feat(C) | xyz - mean | x - (cx*vx + x_off), y - (cy*vy + y_off)] * (slot < n).
+ * m_dev: optional device int32 scalar overriding M (rows >= *m_dev are skipped), may be NULL.
+ */
+PP_API int pp_decorate(const float *voxels, const void *num_points, int num_kind, const void *coors,
+                int coors_kind, int64_t M, const int32_t *m_dev, int P, int C, float vx, float vy,
+                float x_off, float y_off, float *out, pp_stream_t stream);
+
+/*
+ * One PFNLayer in eval mode.  Replaces PFNLayer.forward, model/PointPillars.py:388-423:
+ * Linear(bias=False) -> BatchNorm1d (running stats, folded to scale/shift by the caller)
+ * -> ReLU -> max over all P slots.  last_layer: out (M, U); else out (M, P, 2U).
+ */
+PP_API int pp_pfn_layer(const float *in, int64_t M, int P, int Cin, const float *weight /* (U,Cin) */,
+                 const float *scale, const float *shift, int U, int last_layer, float *out,
+                 pp_stream_t stream);
+
+/*
+ * Fused single-layer PillarFeatureNet (decorate + Linear + BN + ReLU + max + num_points channel).
+ * Replaces PillarFeatureNet.forward, model/PointPillars.py:480-526, for len(feat_channels) == 1.
+ * feat (M, U+1); the last channel is float(num_points) (:526).
+ */
+PP_API int pp_pillar_features(const float *voxels, const void *num_points, int num_kind, const void *coors,
+                       int coors_kind, int64_t M, const int32_t *m_dev, int P, int C, float vx,
+                       float vy, float x_off, float y_off, const float *weight /* (U, C+5) */,
+                       const float *scale, const float *shift, int U, float *feat,
+                       pp_stream_t stream);
+
+/*
+ * Dense scatter.  Replaces SparseMiddleExtractor.forward's
+ * SparseConvTensor(feat, coors, (D,H,W), B).dense().view(N, C*D, H, W), model/PointPillars.py:565-571.
+ * canvas (B, C*D, H, W) f32 is written exactly once (zeros included): no memset needed.
+ * Duplicate coordinates: the highest row index wins (index_put order).
+ * map_ws: workspace of B*D*H*W int32.  batch_index is used only with PP_COORS_XYZ_I32.
+ */
+PP_API size_t pp_scatter_workspace_bytes(int B, int D, int H, int W);
+PP_API int pp_scatter_dense(const float *feat, const void *coors, int coors_kind, int64_t M,
+                     const int32_t *m_dev, int C, int batch_index, int B, int D, int H, int W,
+                     float *canvas, void *map_ws, size_t map_ws_bytes, pp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 3 -- boxes: codec, corners, IoU, NMS.  Boxes are 9-parameter
+ * [x, y, z_bottom, dx, dy, dz, rx, ry, rz] (config.yaml:5).
+ * ---------------------------------------------------------------------------------------- */
+/* BBoxCoder.encode / decode, model/utils.py:276-306 / :309-337.  (K,9) each. */
+PP_API int pp_box_encode(const float *src, const float *dst, int64_t K, float *out, pp_stream_t stream);
+PP_API int pp_box_decode(const float *anchors, const float *deltas, int64_t K, float *out, pp_stream_t stream);
+/* limit_period, model/utils.py:339-350 */
+PP_API int pp_limit_period(const float *val, int64_t n, float offset, float period, float *out,
+                    pp_stream_t stream);
+/* Anchor3DRangeGenerator.grid_anchors for one range, model/utils.py:168-264.
+ * out (D,H,W,S,R,9); sizes (S,3) and rots (R,3) are HOST arrays (tiny, passed by value). */
+PP_API int pp_grid_anchors(const float *range6_host, const float *sizes_host, int S, const float *rots_host,
+                    int R, int D, int H, int W, float *out, pp_stream_t stream);
+/* bbox2corners3D, ops/ops_torch.py:160-256: (N,9) -> (N,8,3) */
+PP_API int pp_box_corners3d(const float *boxes, int64_t N, float *corners, pp_stream_t stream);
+/* bbox2rotated_corners2D, ops/ops_torch.py:13-114: (N,9) -> (N,4) xy bounding rectangle */
+PP_API int pp_box_aabb2d(const float *boxes, int64_t N, float *rect, pp_stream_t stream);
+
+enum { PP_IOU = 0, PP_IOF = 1, PP_GIOU = 2 };
+/* bbox_iou2D, ops/ops_torch.py:538-607: (m,4),(n,4) -> (m,n); same op order, no FMA contraction,
+ * so results are bit-identical to the eager torch ops on identical rectangles. */
+PP_API int pp_bbox_iou2d(const float *b1, int64_t m, const float *b2, int64_t n, int mode, float eps,
+                  float *out, pp_stream_t stream);
+/* iou_jit, ops/ops_numba.py:7-36 (eps added to widths, evaluated in f64 like numba) */
+PP_API int pp_iou_jit(const float *boxes, int64_t N, const float *query, int64_t K, double eps, float *out,
+               pp_stream_t stream);
+
+/*
+ * One class of multiclass_nms, model/utils.py:376-424 (nms_dim == 2 form):
+ * candidates = score > score_thr (strict), sorted by descending score (ties: lower index first),
+ * AABB of the rotated box (bbox2rotated_corners2D), greedy suppression with iou > iou_thr (strict).
+ * scores: element i at scores[i * score_stride].
+ * keep (N) int64: kept ORIGINAL indices in descending-score order; keep_count device int32 scalar.
+ */
+PP_API size_t pp_nms_workspace_bytes(int64_t N);
+PP_API int pp_nms(const float *boxes9, const float *scores, int64_t score_stride, int64_t N, float score_thr,
+           float iou_thr, int64_t *keep, int32_t *keep_count, void *workspace, size_t workspace_bytes,
+           pp_stream_t stream);
+
+/* Stable radix sort of (u32 key, u32 value) pairs, ascending; building block exposed for tests. */
+PP_API size_t pp_sort_workspace_bytes(int64_t n);
+PP_API int pp_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out,
+                      uint32_t *vals_out, int64_t n, void *workspace, size_t workspace_bytes,
+                      pp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PP_B200_H */

@@ -1,0 +1,242 @@
+// Stage 3 element-wise box math: BBoxCoder (model/utils.py:276-337), limit_period (:339-350),
+// anchor grid (:168-264), box corners / xy bounding rectangle (ops/ops_torch.py:13-256) and the
+// axis-aligned IoU matrix (:538-607).  Same op order as the eager torch code with every op rounded
+// separately (-fmad=false + __f*_rn), so IoU on identical rectangles is bit-identical.
+#include "pp_boxes.cuh"
+#include "pp_common.cuh"
+
+namespace pp {
+namespace {
+
+constexpr int BX_THREADS = 256;
+
+__global__ void __launch_bounds__(BX_THREADS)
+box_encode_kernel(const float *__restrict__ src, const float *__restrict__ dst, int64_t K, float *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;
+    if (i >= K) return;
+    float a[9], g[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { a[k] = src[i * 9 + k]; g[k] = dst[i * 9 + k]; }
+    float zg = __fadd_rn(g[2], __fdiv_rn(g[5], 2.0f));
+    float za = __fadd_rn(a[2], __fdiv_rn(a[5], 2.0f));
+    float diag = __fsqrt_rn(__fadd_rn(__fmul_rn(a[3], a[3]), __fmul_rn(a[4], a[4])));
+    float *o = out + i * 9;
+    o[0] = __fdiv_rn(__fsub_rn(g[0], a[0]), diag);
+    o[1] = __fdiv_rn(__fsub_rn(g[1], a[1]), diag);
+    o[2] = __fdiv_rn(__fsub_rn(zg, za), a[5]);
+    o[3] = logf(__fdiv_rn(g[3], a[3]));
+    o[4] = logf(__fdiv_rn(g[4], a[4]));
+    o[5] = logf(__fdiv_rn(g[5], a[5]));
+    o[6] = __fsub_rn(g[6], a[6]);
+    o[7] = __fsub_rn(g[7], a[7]);
+    o[8] = __fsub_rn(g[8], a[8]);
+}
+
+__global__ void __launch_bounds__(BX_THREADS)
+box_decode_kernel(const float *__restrict__ anchors, const float *__restrict__ deltas, int64_t K,
+                  float *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;
+    if (i >= K) return;
+    float a[9], t[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { a[k] = anchors[i * 9 + k]; t[k] = deltas[i * 9 + k]; }
+    float o[9];
+    decode_one(a, t, o);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[i * 9 + k] = o[k];
+}
+
+__global__ void __launch_bounds__(BX_THREADS)
+limit_period_kernel(const float *__restrict__ val, int64_t n, float offset, float period, float *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;
+    if (i >= n) return;
+    float v = val[i];
+    out[i] = __fsub_rn(v, __fmul_rn(floorf(__fadd_rn(__fdiv_rn(v, period), offset)), period));
+}
+
+struct AnchorSpec {
+    float range[6];
+    float sizes[16 * 3];
+    float rots[16 * 3];
+    int S, R, D, H, W;
+};
+
+__global__ void __launch_bounds__(BX_THREADS) grid_anchors_kernel(const AnchorSpec a, int64_t total, float *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;   // one thread per anchor
+    if (i >= total) return;
+    int r = (int)(i % a.R);
+    int64_t t = i / a.R;
+    int s = (int)(t % a.S); t /= a.S;
+    int x = (int)(t % a.W); t /= a.W;
+    int y = (int)(t % a.H);
+    int z = (int)(t / a.H);
+    float *o = out + i * 9;
+    o[0] = linspace_at(a.range[0], a.range[3], a.W, x);
+    o[1] = linspace_at(a.range[1], a.range[4], a.H, y);
+    o[2] = linspace_at(a.range[2], a.range[5], a.D, z);
+    o[3] = a.sizes[s * 3]; o[4] = a.sizes[s * 3 + 1]; o[5] = a.sizes[s * 3 + 2];
+    o[6] = a.rots[r * 3]; o[7] = a.rots[r * 3 + 1]; o[8] = a.rots[r * 3 + 2];
+}
+
+__global__ void __launch_bounds__(BX_THREADS)
+box_corners_kernel(const float *__restrict__ boxes, int64_t N, float *__restrict__ corners, float *__restrict__ rect)
+{
+    int64_t i = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;
+    if (i >= N) return;
+    float b[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) b[k] = boxes[i * 9 + k];
+    float c[8][3];
+    box_corners(b, c);
+    if (corners) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) corners[i * 24 + v * 3 + k] = c[v][k];
+    }
+    if (rect) {
+        float4 r = corners_to_rect(c);
+        reinterpret_cast<float4 *>(rect)[i] = r;
+    }
+}
+
+// (m,n) IoU matrix: one thread per output element, column boxes staged in shared memory.
+__global__ void __launch_bounds__(BX_THREADS)
+iou2d_kernel(const float *__restrict__ b1, int64_t m, const float *__restrict__ b2, int64_t n, int mode, float eps,
+             float *__restrict__ out)
+{
+    __shared__ float4 s_col[BX_THREADS];
+    const int64_t j0 = (int64_t)blockIdx.x * BX_THREADS;
+    const int64_t j = j0 + threadIdx.x;
+    if (j < n) s_col[threadIdx.x] = reinterpret_cast<const float4 *>(b2)[j];
+    __syncthreads();
+    if (j >= n) return;
+    const float4 q = s_col[threadIdx.x];
+    const int64_t i0 = (int64_t)blockIdx.y * 32;
+    for (int64_t i = i0; i < i0 + 32 && i < m; ++i) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(b1) + i);
+        out[i * n + j] = rect_iou(a, q, mode, eps);
+    }
+}
+
+__global__ void __launch_bounds__(BX_THREADS)
+iou_jit_kernel(const float *__restrict__ boxes, int64_t N, const float *__restrict__ query, int64_t K, double eps,
+               float *__restrict__ out)
+{
+    int64_t t = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;
+    if (t >= N * K) return;
+    int64_t nI = t / K, k = t % K;
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + nI);
+    const float4 q = __ldg(reinterpret_cast<const float4 *>(query) + k);
+    // numba: f32 - f32 stays f32, "+ eps" (float64) promotes (ops/ops_numba.py:22-35)
+    double box_area = ((double)__fsub_rn(q.z, q.x) + eps) * ((double)__fsub_rn(q.w, q.y) + eps);
+    double iw = (double)__fsub_rn(fminf(b.z, q.z), fmaxf(b.x, q.x)) + eps;
+    float r = 0.f;
+    if (iw > 0) {
+        double ih = (double)__fsub_rn(fminf(b.w, q.w), fmaxf(b.y, q.y)) + eps;
+        if (ih > 0) {
+            double ua = __dadd_rn(__dmul_rn((double)__fsub_rn(b.z, b.x) + eps, (double)__fsub_rn(b.w, b.y) + eps), box_area);
+            ua = __dsub_rn(ua, __dmul_rn(iw, ih));
+            r = (float)(__dmul_rn(iw, ih) / ua);
+        }
+    }
+    out[t] = r;
+}
+
+}  // namespace
+}  // namespace pp
+
+using namespace pp;
+
+#define GRID1(n) (unsigned)ceil_div((n), BX_THREADS), BX_THREADS, 0, (cudaStream_t)stream
+
+extern "C" int pp_box_encode(const float *src, const float *dst, int64_t K, float *out, pp_stream_t stream)
+{
+    PP_REQUIRE(K >= 0, "K < 0");
+    if (K == 0) return PP_OK;
+    PP_REQUIRE(src && dst && out, "null pointer");
+    box_encode_kernel<<<GRID1(K)>>>(src, dst, K, out);
+    return check_launch("box_encode_kernel");
+}
+
+extern "C" int pp_box_decode(const float *anchors, const float *deltas, int64_t K, float *out, pp_stream_t stream)
+{
+    PP_REQUIRE(K >= 0, "K < 0");
+    if (K == 0) return PP_OK;
+    PP_REQUIRE(anchors && deltas && out, "null pointer");
+    box_decode_kernel<<<GRID1(K)>>>(anchors, deltas, K, out);
+    return check_launch("box_decode_kernel");
+}
+
+extern "C" int pp_limit_period(const float *val, int64_t n, float offset, float period, float *out, pp_stream_t stream)
+{
+    PP_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return PP_OK;
+    PP_REQUIRE(val && out, "null pointer");
+    limit_period_kernel<<<GRID1(n)>>>(val, n, offset, period, out);
+    return check_launch("limit_period_kernel");
+}
+
+extern "C" int pp_grid_anchors(const float *range6_host, const float *sizes_host, int S, const float *rots_host, int R,
+                               int D, int H, int W, float *out, pp_stream_t stream)
+{
+    PP_REQUIRE(range6_host && sizes_host && rots_host && out, "null pointer");
+    PP_REQUIRE(S > 0 && S <= 16 && R > 0 && R <= 16, "1..16 sizes / rotations supported");
+    PP_REQUIRE(D > 0 && H > 0 && W > 0, "bad feature map");
+    AnchorSpec a;
+    for (int i = 0; i < 6; ++i) a.range[i] = range6_host[i];
+    for (int i = 0; i < S * 3; ++i) a.sizes[i] = sizes_host[i];
+    for (int i = 0; i < R * 3; ++i) a.rots[i] = rots_host[i];
+    a.S = S; a.R = R; a.D = D; a.H = H; a.W = W;
+    int64_t total = (int64_t)D * H * W * S * R;
+    grid_anchors_kernel<<<GRID1(total)>>>(a, total, out);
+    return check_launch("grid_anchors_kernel");
+}
+
+extern "C" int pp_box_corners3d(const float *boxes, int64_t N, float *corners, pp_stream_t stream)
+{
+    PP_REQUIRE(N >= 0, "N < 0");
+    if (N == 0) return PP_OK;
+    PP_REQUIRE(boxes && corners, "null pointer");
+    box_corners_kernel<<<GRID1(N)>>>(boxes, N, corners, nullptr);
+    return check_launch("box_corners_kernel");
+}
+
+extern "C" int pp_box_aabb2d(const float *boxes, int64_t N, float *rect, pp_stream_t stream)
+{
+    PP_REQUIRE(N >= 0, "N < 0");
+    if (N == 0) return PP_OK;
+    PP_REQUIRE(boxes && rect, "null pointer");
+    PP_REQUIRE((uintptr_t)rect % 16 == 0, "rect must be 16-byte aligned");
+    box_corners_kernel<<<GRID1(N)>>>(boxes, N, nullptr, rect);
+    return check_launch("box_corners_kernel");
+}
+
+extern "C" int pp_bbox_iou2d(const float *b1, int64_t m, const float *b2, int64_t n, int mode, float eps, float *out,
+                             pp_stream_t stream)
+{
+    PP_REQUIRE(m >= 0 && n >= 0, "negative size");
+    PP_REQUIRE(mode == PP_IOU || mode == PP_IOF || mode == PP_GIOU, "Unsupported mode");
+    if (m == 0 || n == 0) return PP_OK;
+    PP_REQUIRE(b1 && b2 && out, "null pointer");
+    PP_REQUIRE((uintptr_t)b1 % 16 == 0 && (uintptr_t)b2 % 16 == 0, "boxes must be 16-byte aligned");
+    PP_REQUIRE(ceil_div(m, 32) < 65536, "too many rows for one launch");
+    dim3 grid((unsigned)ceil_div(n, BX_THREADS), (unsigned)ceil_div(m, 32));
+    iou2d_kernel<<<grid, BX_THREADS, 0, (cudaStream_t)stream>>>(b1, m, b2, n, mode, eps, out);
+    return check_launch("iou2d_kernel");
+}
+
+extern "C" int pp_iou_jit(const float *boxes, int64_t N, const float *query, int64_t K, double eps, float *out,
+                          pp_stream_t stream)
+{
+    PP_REQUIRE(N >= 0 && K >= 0, "negative size");
+    if (N == 0 || K == 0) return PP_OK;
+    PP_REQUIRE(boxes && query && out, "null pointer");
+    PP_REQUIRE((uintptr_t)boxes % 16 == 0 && (uintptr_t)query % 16 == 0, "boxes must be 16-byte aligned");
+    iou_jit_kernel<<<GRID1(N * K)>>>(boxes, N, query, K, eps, out);
+    return check_launch("iou_jit_kernel");
+}

@@ -1,0 +1,79 @@
+// Shared helpers for libpp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pp_b200.h"
+
+#define PP_INF_POS 0x7F7F7F7F  // "empty" marker that cudaMemsetAsync(0x7F) produces for int32
+
+namespace pp {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+inline int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return PP_ERR_CUDA;
+    }
+    count_launch();
+    return PP_OK;
+}
+
+#define PP_CUDA_TRY(expr)                                                        \
+    do {                                                                         \
+        cudaError_t e__ = (expr);                                                \
+        if (e__ != cudaSuccess) {                                                \
+            pp::set_error("%s: %s", #expr, cudaGetErrorString(e__));             \
+            return PP_ERR_CUDA;                                                  \
+        }                                                                        \
+    } while (0)
+
+#define PP_REQUIRE(cond, msg)                                                    \
+    do {                                                                         \
+        if (!(cond)) {                                                           \
+            pp::set_error("%s: %s", __func__, msg);                              \
+            return PP_ERR_INVALID;                                               \
+        }                                                                        \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace.
+struct Arena {
+    char *base;
+    size_t off, cap;
+    Arena(void *p, size_t bytes) : base((char *)p), off(0), cap(bytes) {}
+    template <typename T> T *take(size_t n)
+    {
+        size_t o = align_up(off);
+        off = o + n * sizeof(T);
+        return (T *)(base + o);
+    }
+    bool ok() const { return off <= cap; }
+};
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// float -> uint32 whose unsigned order equals the float order (finite values; -0 < +0)
+__device__ __forceinline__ uint32_t ordered_bits(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+// L2-coherent loads (bypass the non-coherent L1) for data other CTAs are updating
+__device__ __forceinline__ int ld_cg(const int *p) { return __ldcg(p); }
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+}  // namespace pp

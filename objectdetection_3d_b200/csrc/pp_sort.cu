@@ -1,0 +1,211 @@
+// Stable LSD radix sort of (u32 key, u32 value) pairs: one histogram pass + 4 single-sweep digit
+// passes with decoupled look-back ("onesweep" structure, hand-written; no CUB).
+//
+// Used by the voxelizer's reflectance pre-order (ops/ops_numba.py:262) and by NMS score ordering
+// (model/utils.py:398).  Stability is what defines the documented tie rule (lower original index
+// first).  HBM-bound: 4 x (read keys+vals, write keys+vals).
+#include "pp_common.cuh"
+#include "pp_sort.cuh"
+
+namespace pp {
+
+namespace {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int NPASS = 4;
+
+constexpr uint32_t FLAG_AGG = 1u << 30;
+constexpr uint32_t FLAG_PREFIX = 2u << 30;
+constexpr uint32_t FLAG_MASK = 3u << 30;
+constexpr uint32_t VAL_MASK = ~FLAG_MASK;
+
+// All four digit histograms in one pass over the keys.
+__global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const uint32_t *__restrict__ keys, int64_t n,
+                                                                  uint32_t *__restrict__ hist /* [4][256] */)
+{
+    __shared__ uint32_t sh[NPASS * RADIX];
+    for (int i = threadIdx.x; i < NPASS * RADIX; i += SORT_THREADS) sh[i] = 0;
+    __syncthreads();
+    int64_t stride = (int64_t)gridDim.x * SORT_THREADS;
+    for (int64_t i = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x; i < n; i += stride) {
+        uint32_t k = keys[i];
+#pragma unroll
+        for (int p = 0; p < NPASS; ++p) atomicAdd(&sh[p * RADIX + ((k >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NPASS * RADIX; i += SORT_THREADS)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int pass,
+                 const uint32_t *__restrict__ hist /* this pass: [256] */, uint32_t *status /* [tiles][256] */,
+                 uint32_t *ticket)
+{
+    constexpr int TILE = SORT_THREADS * ITEMS;
+    __shared__ uint32_t warp_hist[SORT_WARPS][RADIX + 1];
+    __shared__ uint32_t digit_off[RADIX];   // global offset of this tile's first key of each digit
+    __shared__ uint32_t scan_tmp[SORT_WARPS];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < SORT_WARPS * (RADIX + 1); i += SORT_THREADS) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t tile_base = (int64_t)tile * TILE;
+    const int64_t warp_base = tile_base + (int64_t)warp * (32 * ITEMS);
+    const int shift = pass * RADIX_BITS;
+
+    uint32_t key[ITEMS];
+    uint32_t rank[ITEMS];   // rank of the key among equal digits inside its warp (stable)
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        int64_t idx = warp_base + r * 32 + lane;
+        bool valid = idx < n;
+        key[r] = valid ? keys_in[idx] : 0xFFFFFFFFu;
+        uint32_t d = valid ? ((key[r] >> shift) & (RADIX - 1)) : (uint32_t)RADIX;
+        unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        uint32_t pre = warp_hist[warp][d];
+        __syncwarp();
+        if ((peers & lanemask_lt()) == 0) warp_hist[warp][d] = pre + __popc(peers);
+        __syncwarp();
+        rank[r] = pre + __popc(peers & lanemask_lt());
+    }
+    __syncthreads();
+
+    // thread d owns digit d: exclusive scan over the warps, then decoupled look-back over tiles
+    {
+        const int d = tid;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            uint32_t c = warp_hist[w][d];
+            warp_hist[w][d] = run;
+            run += c;
+        }
+        const uint32_t tile_count = run;
+        uint32_t *my = status + (size_t)tile * RADIX + d;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            atomicExch(my, FLAG_PREFIX | tile_count);
+        } else {
+            atomicExch(my, FLAG_AGG | tile_count);
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                uint32_t s = *((volatile uint32_t *)(status + (size_t)t * RADIX + d));
+                if ((s & FLAG_MASK) == 0) continue;   // predecessor not published yet
+                excl += s & VAL_MASK;
+                if ((s & FLAG_MASK) == FLAG_PREFIX) break;
+                --t;
+            }
+            atomicExch(my, FLAG_PREFIX | (excl + tile_count));
+        }
+        // exclusive scan of the global digit histogram (256 values, one per thread)
+        uint32_t h = hist[d];
+        uint32_t incl = h;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) scan_tmp[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += scan_tmp[w];
+        digit_off[d] = wbase + incl - h + excl;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        int64_t idx = warp_base + r * 32 + lane;
+        if (idx < n) {
+            uint32_t d = (key[r] >> shift) & (RADIX - 1);
+            uint32_t dst = digit_off[d] + warp_hist[warp][d] + rank[r];
+            keys_out[dst] = key[r];
+            vals_out[dst] = vals_in ? vals_in[idx] : (uint32_t)idx;
+        }
+    }
+}
+
+struct SortWs {
+    uint32_t *hist, *tickets, *status;
+    uint32_t *keys_tmp, *vals_tmp;
+    size_t zero_bytes;
+    int tiles;
+};
+
+constexpr int SORT_ITEMS = 8;
+
+SortWs carve(void *ws, int64_t n, size_t *total)
+{
+    SortWs s;
+    s.tiles = (int)ceil_div(n > 0 ? n : 1, (int64_t)SORT_THREADS * SORT_ITEMS);
+    Arena a(ws, (size_t)-1);
+    s.hist = a.take<uint32_t>(NPASS * RADIX);
+    s.tickets = a.take<uint32_t>(64);
+    s.status = a.take<uint32_t>((size_t)NPASS * s.tiles * RADIX);
+    s.zero_bytes = a.off;
+    s.keys_tmp = a.take<uint32_t>((size_t)(n > 0 ? n : 1));
+    s.vals_tmp = a.take<uint32_t>((size_t)(n > 0 ? n : 1));
+    *total = align_up(a.off);
+    return s;
+}
+
+}  // namespace
+
+size_t sort_workspace_bytes(int64_t n)
+{
+    size_t total;
+    carve(nullptr, n, &total);
+    return total;
+}
+
+int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
+                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    if (n <= 0) return PP_OK;
+    PP_REQUIRE(n < (1ll << 30), "n must be < 2^30");
+    size_t total;
+    SortWs s = carve(ws, n, &total);
+    if (ws_bytes < total) {
+        set_error("sort workspace too small: %zu < %zu", ws_bytes, total);
+        return PP_ERR_WORKSPACE;
+    }
+    PP_CUDA_TRY(cudaMemsetAsync(ws, 0, s.zero_bytes, st));
+    int hist_blocks = (int)(ceil_div(n, SORT_THREADS * 16) < 148 * 4 ? ceil_div(n, SORT_THREADS * 16) : 148 * 4);
+    sort_hist_kernel<<<hist_blocks, SORT_THREADS, 0, st>>>(keys_in, n, s.hist);
+    if (int rc = check_launch("sort_hist_kernel")) return rc;
+    const uint32_t *kin = keys_in, *vin = vals_in;
+    for (int p = 0; p < NPASS; ++p) {
+        uint32_t *kout = (p & 1) ? keys_out : s.keys_tmp;
+        uint32_t *vout = (p & 1) ? vals_out : s.vals_tmp;
+        sort_pass_kernel<SORT_ITEMS><<<s.tiles, SORT_THREADS, 0, st>>>(
+            kin, vin, kout, vout, n, p, s.hist + p * RADIX, s.status + (size_t)p * s.tiles * RADIX, s.tickets + p);
+        if (int rc = check_launch("sort_pass_kernel")) return rc;
+        kin = kout;
+        vin = vout;
+    }
+    return PP_OK;
+}
+
+}  // namespace pp
+
+extern "C" size_t pp_sort_workspace_bytes(int64_t n) { return pp::sort_workspace_bytes(n); }
+
+extern "C" int pp_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out,
+                                 uint32_t *vals_out, int64_t n, void *workspace, size_t workspace_bytes,
+                                 pp_stream_t stream)
+{
+    PP_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return PP_OK;
+    PP_REQUIRE(keys_in && keys_out && vals_out && workspace, "null pointer");
+    return pp::sort_pairs_u32(keys_in, vals_in, keys_out, vals_out, n, workspace, workspace_bytes,
+                              (cudaStream_t)stream);
+}

@@ -1,0 +1,273 @@
+"""GPU: the CUDA path (through the C ABI of libpp_b200.so) against the golden fixtures produced by the
+reference and against the CPU oracle on seeded inputs.  Integer outputs bit-exact (T0); FP32 within
+1e-5 relative (T1) -- or bit-exact against the oracle where the op order is identical."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close_t1, golden
+from test_oracle_golden import VOX, vox_args
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pp():
+    import objectdetection_3d_b200 as pkg
+    from objectdetection_3d_b200 import _lib, model_utils, ops_numba, ops_torch, pointpillars
+    _lib.load()
+    assert torch.cuda.is_available()
+    pkg.ops_numba, pkg.ops_torch, pkg.model_utils, pkg.pointpillars = ops_numba, ops_torch, model_utils, pointpillars
+    return pkg
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+# ------------------------------------------------------------------------------------------ sort
+@pytest.mark.parametrize("n", [1, 31, 2048, 2049, 100_003, 1_000_000])
+def test_radix_sort_stable(pp, n):
+    import ctypes
+    from objectdetection_3d_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 2 ** 32 if n % 2 else 1000, size=n, dtype=np.uint64).astype(np.uint32)
+    k = cu(keys.view(np.int32))
+    ko, vo = torch.empty_like(k), torch.empty_like(k)
+    ws = torch.empty(int(lib.pp_sort_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+    rc = lib.pp_sort_pairs_u32(k.data_ptr(), None, ko.data_ptr(), vo.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(vo.cpu().numpy().view(np.uint32), order.astype(np.uint32))
+    assert np.array_equal(ko.cpu().numpy().view(np.uint32), keys[order])
+
+
+# ------------------------------------------------------------------------------------------ voxelize
+@pytest.mark.parametrize("name", VOX)
+def test_voxelize_golden(pp, oracle, name):
+    g = golden(name)
+    vs, rg, P, cap, refl = vox_args(g)
+    has_ties = name == "vox_model_ties"
+    if refl and not has_ties:
+        v, c, n = pp.ops_numba.points_to_voxel(g["points"].copy(), vs, rg, P, cap, True)
+    elif refl:      # replay the reference's (numba quicksort) tie order
+        perm = oracle.numba_argsort_desc(g["points"][:, 3])
+        v, c, n = pp.ops_numba.points_to_voxel(g["points"].copy(), vs, rg, P, cap, True, perm=perm)
+    else:           # shuffle variant: replay the order the reference left in the caller's array
+        v, c, n = pp.ops_numba.points_to_voxel(g["points_after"].copy(), vs, rg, P, cap, False,
+                                               perm=np.arange(len(g["points"])))
+    assert v.dtype == np.float32 and c.dtype == np.int32 and n.dtype == np.int32
+    assert np.array_equal(c, g["coors"])
+    assert np.array_equal(n, g["num"])
+    assert np.array_equal(v.view(np.uint32), g["voxels"].view(np.uint32))
+
+
+def test_voxelize_ties_documented_rule(pp, oracle):
+    """With ties the GPU order is (reflectance desc, original index asc): equals the oracle fed with
+    that permutation."""
+    g = golden("vox_model_ties")
+    vs, rg, P, cap, _ = vox_args(g)
+    pts = g["points"]
+    v, c, n = pp.ops_numba.points_to_voxel(pts.copy(), vs, rg, P, cap, True)
+    perm = np.argsort(-pts[:, 3], kind="stable")
+    ov, oc, on = oracle.points_to_voxel(pts, vs, rg, P, cap, False, perm=perm)
+    assert np.array_equal(c, oc) and np.array_equal(n, on) and np.array_equal(v, ov)
+
+
+@pytest.mark.parametrize("kind,n,cap,P", [("dense", 1_000_000, 12000, 32), ("uniform", 1_000_000, 12000, 32),
+                                           ("dense", 300_000, 3000, 32), ("forest", 120_000, 7500000, 50)])
+def test_voxelize_full_size_vs_oracle(pp, oracle, kind, n, cap, P):
+    from objectdetection_3d_b200 import synth
+    if kind == "forest":
+        g, pts = synth.G_REF, synth.forest_tile(n=n)
+    else:
+        g = synth.G_KITTI
+        pts = synth.dense_tile(n=n) if kind == "dense" else synth.uniform_tile(n=n, margin=0.02)
+    vs = np.array(g["voxel_size"], dtype=np.float32)
+    rg = np.array(g["point_cloud_range"], dtype=np.float64)
+    for refl in (True, False):
+        if refl:
+            v, c, m = pp.ops_numba.points_to_voxel(pts.copy(), vs, rg, P, cap, True)
+        else:
+            v, c, m = pp.ops_numba.points_to_voxel(pts.copy(), vs, rg, P, cap, False, perm=np.arange(n))
+        ov, oc, om = oracle.points_to_voxel(pts, vs, rg, P, cap, refl)
+        assert np.array_equal(c, oc) and np.array_equal(m, om) and np.array_equal(v, ov), (kind, refl)
+    # size-independent properties: every kept row is an input point; counts bounded
+    assert (m >= 1).all() and (m <= P).all()
+
+
+def test_voxelize_edge_cases(pp):
+    from objectdetection_3d_b200 import synth
+    g = synth.G_KITTI
+    vs, rg = np.array(g["voxel_size"], dtype=np.float32), np.array(g["point_cloud_range"])
+    v, c, n = pp.ops_numba.points_to_voxel(np.zeros((0, 4), np.float32), vs, rg, 32, 100, True)
+    assert v.shape == (0, 32, 4) and c.shape == (0, 3) and n.shape == (0,)
+    far = np.full((100, 4), 1e6, np.float32)
+    v, c, n = pp.ops_numba.points_to_voxel(far, vs, rg, 32, 100, True)
+    assert v.shape[0] == 0
+    one = np.array([[1.0, 1.0, 0.0, 0.5]] * 100, np.float32)
+    v, c, n = pp.ops_numba.points_to_voxel(one, vs, rg, 32, 100, True)
+    assert v.shape[0] == 1 and n[0] == 32 and (v[0] == one[0]).all()
+
+
+def test_module_voxelization_device(pp, oracle):
+    from objectdetection_3d_b200 import synth
+    g = synth.G_KITTI
+    pts = synth.dense_tile(n=200_000, seed=5)
+    mod = pp.pointpillars.PointPillarsVoxelization("cuda", g["voxel_size"], g["point_cloud_range"], 32, 12000)
+    v, c, n = mod(pts)
+    ov, oc, on = oracle.pointpillars_voxelization(pts, g["voxel_size"], g["point_cloud_range"], 32, 12000)
+    assert c.dtype == torch.int64 and n.dtype == torch.int64 and v.is_cuda
+    assert np.array_equal(v.cpu().numpy(), ov) and np.array_equal(c.cpu().numpy(), oc) and np.array_equal(n.cpu().numpy(), on)
+
+
+# ------------------------------------------------------------------------------------------ PFN / scatter
+@pytest.mark.parametrize("name", ["pfn_single64", "pfn_two_layer"])
+def test_pfn_golden_and_oracle(pp, oracle, name):
+    g = golden(name)
+    vs, rg = g["voxel_size"].tolist(), g["point_cloud_range"].tolist()
+    nl = int(g["n_layers"])
+    feat = [g["w%d" % i].shape[0] * (1 if i == nl - 1 else 2) + (1 if i == nl - 1 else 0) for i in range(nl)]
+    net = pp.pointpillars.PillarFeatureNet(4, feat, vs, rg).cuda().eval()
+    for i, l in enumerate(net.pfn_layers):
+        with torch.no_grad():
+            l.linear.weight.copy_(cu(g["w%d" % i])); l.norm.weight.copy_(cu(g["gamma%d" % i]))
+            l.norm.bias.copy_(cu(g["beta%d" % i])); l.norm.running_mean.copy_(cu(g["mean%d" % i]))
+            l.norm.running_var.copy_(cu(g["var%d" % i]))
+    voxels, num, coors = cu(g["voxels"]), cu(g["num"]), cu(g["coors"])
+    scale = float(np.abs(g["voxels"]).max())
+    dec = net.decorate(voxels, num, coors).cpu().numpy()
+    assert_close_t1(dec, g["decorated"], atol=1e-5 * scale, what="decorated vs reference")
+    odec = oracle.decorate(g["voxels"], g["num"], g["coors"], vs[0], vs[1], vs[0] / 2 + rg[0], vs[1] / 2 + rg[1])
+    assert np.array_equal(dec.view(np.uint32), odec.view(np.uint32)), "decoration is bit-exact vs the oracle"
+    with torch.no_grad():
+        out = net(voxels, num, coors).cpu().numpy()
+    assert_close_t1(out, g["out"], atol=1e-5 * scale, what="pfn vs reference")
+    layers = [dict(weight=g["w%d" % i], gamma=g["gamma%d" % i], beta=g["beta%d" % i], mean=g["mean%d" % i],
+                   var=g["var%d" % i]) for i in range(nl)]
+    oout = oracle.pillar_feature_net(g["voxels"], g["num"], g["coors"], layers, vs, rg)
+    assert_close_t1(out, oout, atol=1e-6 * scale, what="pfn vs oracle")
+    # int32 inputs (what the voxelizer produces natively) give the same result
+    with torch.no_grad():
+        out32 = net(voxels, num.int(), coors.int()).cpu().numpy()
+    assert np.array_equal(out32, out)
+    # scatter
+    H, W = g["canvas_hw"].tolist()
+    sc = pp.pointpillars.SparseMiddleExtractor([1, H, W])
+    canvas = sc(cu(g["out"]), coors, 1).cpu().numpy()
+    assert np.array_equal(canvas, g["canvas"])
+    canvas = sc(cu(g["out"]), coors.int(), 1).cpu().numpy()
+    assert np.array_equal(canvas, g["canvas"])
+
+
+def test_scatter_3d_batched_and_backward(pp, oracle):
+    rng = np.random.default_rng(3)
+    B, D, H, W, C, M = 3, 4, 37, 41, 5, 900          # H*W not a multiple of 4 -> scalar store path
+    lin = rng.choice(B * D * H * W, size=M, replace=False)
+    coors = np.stack(np.unravel_index(lin, (B, D, H, W)), 1).astype(np.int32)
+    feat = rng.normal(size=(M, C)).astype(np.float32)
+    sc = pp.pointpillars.SparseMiddleExtractor([D, H, W])
+    f = cu(feat).requires_grad_(True)
+    canvas = sc(f, cu(coors), B)
+    assert np.array_equal(canvas.detach().cpu().numpy(), oracle.scatter_dense(feat, coors, B, D, H, W))
+    w = torch.randn_like(canvas)
+    (canvas * w).sum().backward()
+    c = coors.astype(np.int64)
+    expect = w.view(B, C, D, H, W).cpu().numpy()[c[:, 0], :, c[:, 1], c[:, 2], c[:, 3]]
+    assert np.array_equal(f.grad.cpu().numpy(), expect)
+
+
+# ------------------------------------------------------------------------------------------ boxes
+def test_boxes_iou_golden(pp, oracle):
+    g = golden("boxes_iou")
+    b = cu(g["boxes"])
+    rect = pp.ops_torch.bbox2rotated_corners2D(b).cpu().numpy()
+    assert_close_t1(rect, g["rect"], what="aabb")
+    assert_close_t1(pp.ops_torch.bbox2corners3D(b).cpu().numpy(), g["corners"], atol=2e-6, what="corners")
+    r = cu(g["rect"])
+    assert np.array_equal(pp.ops_torch.bbox_iou2D(r[:200], r[200:500]).cpu().numpy(), g["iou"])
+    assert np.array_equal(pp.ops_torch.bbox_iou2D(r[:50], r[200:300], "iof").cpu().numpy(), g["iof"])
+    assert np.array_equal(pp.ops_torch.bbox_iou2D(r[:50], r[200:300], "giou").cpu().numpy(), g["giou"])
+    assert np.array_equal(pp.ops_numba.iou_jit(g["rect"][:40], g["rect"][300:360], 0.0), g["iou_jit"])
+    assert np.array_equal(pp.ops_numba.iou_jit(g["rect"][:40], g["rect"][300:360], 1.0), g["iou_jit_eps1"])
+    with pytest.raises(AssertionError):
+        pp.ops_torch.bbox_iou2D(r[:5], r[:5], "bad")
+    assert pp.ops_torch.bbox_iou2D(r[:0], r[:5]).shape == (0, 5)
+
+
+def test_codec_anchors_golden(pp, oracle):
+    from objectdetection_3d_b200 import synth
+    g = golden("codec")
+    enc = pp.model_utils.BBoxCoder.encode(cu(g["anchors"]), cu(g["gts"])).cpu().numpy()
+    dec = pp.model_utils.BBoxCoder.decode(cu(g["anchors"]), cu(g["deltas"])).cpu().numpy()
+    assert_close_t1(enc, g["encoded"], what="encode")
+    assert_close_t1(dec, g["decoded"], what="decode")
+    assert_close_t1(pp.model_utils.limit_period(cu(g["val"]), 1, np.pi).cpu().numpy(), g["limit_1_pi"], atol=2e-6)
+    assert_close_t1(pp.model_utils.limit_period(cu(g["val"]), 0.5, 2 * np.pi).cpu().numpy(), g["limit_05_2pi"], atol=2e-6)
+    a = golden("anchors")
+    gen = pp.model_utils.Anchor3DRangeGenerator([[0, 0, 0, 40.0, 40.0, 30.0]], synth.ANCHOR_SIZES,
+                                                synth.ANCHOR_ROTATIONS, 9)
+    got = gen.grid_anchors((5, 7), device="cuda").cpu().numpy()
+    assert got.shape == a["a57"].shape
+    assert_close_t1(got, a["a57"], what="anchors")
+    gen2 = pp.model_utils.Anchor3DRangeGenerator([[0, -39.68, -1.78, 69.12, 39.68, -1.78]], [[1.6, 3.9, 1.56]],
+                                                 [[0, 0, 0], [0, 0, 1.57]], 9)
+    assert_close_t1(gen2.grid_anchors((31, 27), device="cuda").cpu().numpy(), a["a_kitti"], what="anchors kitti")
+
+
+# ------------------------------------------------------------------------------------------ NMS
+def test_multiclass_nms_golden(pp):
+    g = golden("nms_multiclass")
+    b, s = cu(g["boxes"]), cu(g["scores"])
+    for si, sthr in enumerate(g["score_thrs"].tolist()):
+        for ii, ithr in enumerate(g["iou_thrs"].tolist()):
+            keep = pp.model_utils.multiclass_nms(b, s, sthr, ithr, 2)
+            for c in range(2):
+                assert keep[c].dtype == torch.int64
+                assert np.array_equal(keep[c].cpu().numpy(), g["keep_s%d_i%d_c%d" % (si, ii, c)]), (sthr, ithr, c)
+
+
+@pytest.mark.parametrize("n,extent", [(20_000, 40.0), (20_000, 200.0), (5000, 10.0), (65, 3.0), (1, 1.0)])
+def test_nms_full_size_vs_oracle(pp, oracle, n, extent):
+    from objectdetection_3d_b200 import synth
+    boxes, scores = synth.nms_boxes(n=n, seed=4, extent=extent)
+    b, s = cu(boxes), cu(scores)
+    for sthr, ithr in ((0.05, 1e-5), (0.3, 0.1), (0.5, 0.5), (0.99999, 0.1)):
+        got = pp.model_utils.multiclass_nms(b, s, sthr, ithr, 2)[0].cpu().numpy()
+        # the oracle NMS is fed the rectangles the GPU computed, so the keep list must be IDENTICAL
+        # (T0 "given identical rectangles"); rectangles themselves are T1-checked above
+        cand = np.nonzero(scores[:, 0] > np.float32(sthr))[0]
+        order = cand[np.argsort(-scores[cand, 0], kind="stable")]
+        rect = pp.ops_torch.bbox2rotated_corners2D(b).cpu().numpy()
+        keep = oracle.nms_sorted(rect[order], ithr)
+        assert np.array_equal(got, order[keep]), (n, extent, sthr, ithr)
+        # properties: descending score; no kept pair overlaps above thr
+        assert (np.diff(scores[got, 0]) < 0).all()
+        if 0 < len(got) <= 3000:
+            iou = oracle.bbox_iou2D(rect[got], rect[got])
+            np.fill_diagonal(iou, 0)
+            assert not (iou > np.float32(ithr)).any()
+
+
+def test_head_golden(pp):
+    """Anchor3DHead.get_bboxes_single / assign_bboxes against the reference's outputs."""
+    from objectdetection_3d_b200 import synth
+    g = golden("head")
+    head = pp.pointpillars.Anchor3DHead(num_classes=1, in_channels=8, nms_dim=2, nms_pre=300, nms_thresh=0.1,
+                                        score_thr=0.3, ranges=[[0, 0, 0, 40.0, 40.0, 30.0]], sizes=synth.ANCHOR_SIZES,
+                                        rotations=synth.ANCHOR_ROTATIONS, iou_thr=[[0.08, 0.2]]).cuda()
+    with torch.no_grad():
+        b, s, l = head.get_bboxes_single(cu(g["cls"]), cu(g["reg"]), cu(g["dirs"]))
+    assert b.shape == g["bboxes"].shape
+    assert_close_t1(s.cpu().numpy(), g["scores"], what="scores")
+    assert_close_t1(b.cpu().numpy(), g["bboxes"], atol=1e-5, what="bboxes")
+    assert np.array_equal(l.numpy(), g["labels"])
+    with torch.no_grad():
+        ab, ti, pi, ni = head.assign_bboxes(cu(g["reg"]).unsqueeze(0), [cu(g["gts"])])
+    assert np.array_equal(ti.cpu().numpy(), g["target_idx"])
+    assert np.array_equal(pi.cpu().numpy(), g["pos_idx"])
+    assert np.array_equal(ni.cpu().numpy(), g["neg_idx"])
+    assert_close_t1(ab.cpu().numpy(), g["assigned"], atol=1e-5, what="assigned")
