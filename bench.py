@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the PointPillars pre/post-processing hot path (BASELINE.json metric:
+voxelize+scatter+NMS frames/s).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One step = one frame of BASELINE.json configs[1] (a 1M-point dense tile, G_kitti geometry: 12k pillars
+x 32 points, 432x496 canvas, reflectance pre-order as on the model path) through
+voxelize -> decorate+PFN -> dense scatter, followed by one class of NMS on 20 000 boxes.  For N > 1 every
+rank runs its own frames (per-frame data parallelism, no collective on the data path, weak scaling);
+timing is CUDA events per rank, max over ranks.  See DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_POINTS = 1_000_000
+N_BOXES = 20_000
+NMS_SCORE_THR = 0.0      # every one of the 20k boxes is a candidate (scores are (perm + 0.5) / N > 0)
+NMS_IOU_THR = 0.1
+NMS_EXTENT = 40.0        # dense case of SURVEY.md 8(d) NMS20k
+RING_TILES = 8           # distinct input tiles per GPU  (8 x 16 MB)
+RING_CANVAS = 4          # distinct output canvases      (4 x 54.9 MB)  -> working set > 126 MB L2
+WORKLOAD = "D1M tile (1e6 pts, 0.16 m pillars, 12000x32, 432x496 canvas, reflectance order) + NMS20k dense"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def base_config(n_gpus):
+    return {"workload": WORKLOAD, "n_points": N_POINTS, "n_boxes": N_BOXES, "frames_per_step_per_gpu": 1,
+            "nms": {"score_thr": NMS_SCORE_THR, "iou_thr": NMS_IOU_THR, "extent_m": NMS_EXTENT},
+            "parallelism": "frames sharded over %d GPU(s), no collective" % n_gpus,
+            "l2": "inputs larger than L2: ring of %d tiles + %d canvases per GPU (%.0f MB)" %
+                  (RING_TILES, RING_CANVAS, RING_TILES * 16.0 + RING_CANVAS * 54.85)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def make_frame(seed):
+    from objectdetection_3d_b200 import synth
+    pts = synth.dense_tile(n=N_POINTS, seed=seed)
+    boxes, scores = synth.nms_boxes(n=N_BOXES, seed=seed + 7, extent=NMS_EXTENT)
+    return pts, boxes, scores
+
+
+def cpu_frame(O, geom, pfn, pts, boxes, scores):
+    """The reference's CPU path for one frame, through the oracle port (oracle/pp_oracle.c)."""
+    v, c, n = O.pointpillars_voxelization(pts, geom["voxel_size"], geom["point_cloud_range"],
+                                          geom["max_voxel_points"], geom["max_voxels"])
+    coors = np.concatenate([np.zeros((len(c), 1), np.int64), c], 1)
+    feat = O.pillar_feature_net(v, n, coors, [pfn], geom["voxel_size"], geom["point_cloud_range"])
+    canvas = O.scatter_dense(feat, coors.astype(np.int32), 1, 1, 496, 432)
+    keep = O.multiclass_nms(boxes, scores, NMS_SCORE_THR, NMS_IOU_THR, 2)[0]
+    return canvas, keep
+
+
+def cpu_baseline(seconds):
+    """Oracle port on the host cores, single thread (the reference's numba kernels are single-threaded,
+    ops/ops_numba.py:171,242); a bounded sample of whole frames."""
+    from objectdetection_3d_b200 import synth
+    from oracle import oracle as O
+    O.lib()
+    geom, pfn = synth.G_KITTI, synth.pfn_params(9, 63, seed=5)
+    pts, boxes, scores = make_frame(3000)
+    cpu_frame(O, geom, pfn, pts[:50_000], boxes[:2000], scores[:2000])       # warm-up (page-in)
+    t0 = time.perf_counter()
+    frames = 0
+    while frames < 3 or (time.perf_counter() - t0 < seconds and frames < 64):
+        cpu_frame(O, geom, pfn, pts, boxes, scores)
+        frames += 1
+    dt = time.perf_counter() - t0
+    return {"value": frames / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": "%d whole frames (same D1M tile + NMS20k) in %.1f s, oracle/pp_oracle.c single thread" % (frames, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: the reference is
+    pure Python and its checkout is not on the GPU box) on all host threads, one frame per thread per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from objectdetection_3d_b200 import synth
+    from oracle import oracle as O
+    O.lib()
+    geom, pfn = synth.G_KITTI, synth.pfn_params(9, 63, seed=5)
+    threads = max(1, min(os.cpu_count() or 1, 32))
+    frames = [make_frame(3000 + i) for i in range(min(threads, 4))]
+    pool = ThreadPoolExecutor(threads)
+
+    def step():
+        futs = [pool.submit(cpu_frame, O, geom, pfn, *frames[i % len(frames)]) for i in range(threads)]
+        for f in futs:
+            f.result()
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    # bound the run: each step is `threads` whole frames; cap the timed steps so the run ends in minutes
+    t_probe = time.perf_counter(); step(); per_step = time.perf_counter() - t_probe
+    steps = max(1, min(args.steps, int(120.0 / max(per_step, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = steps * threads / dt
+    line = {"impl": "reference", "metric": "voxelize+scatter+NMS frames/s", "value": value, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(base_config(args.gpus), frames_per_step=threads),
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": "%d steps x %d frames (one per host thread), oracle/pp_oracle.c" % (steps, threads)},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from objectdetection_3d_b200 import _lib, pipeline, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    K, W = args.steps, max(args.warmup, 3)
+    geom, pfn = synth.G_KITTI, synth.pfn_params(9, 63, seed=5)
+
+    # B64-style sharding: frame i of the job -> rank i mod world; every rank holds RING_TILES distinct tiles
+    host_pts, host_boxes, host_scores = [], [], []
+    for i in range(RING_TILES):
+        p, b, s = make_frame(3000 + rank + world * i)
+        host_pts.append(torch.from_numpy(p).pin_memory())
+        host_boxes.append(torch.from_numpy(b).pin_memory())
+        host_scores.append(torch.from_numpy(s).pin_memory())
+    d_pts = [t.to(dev) for t in host_pts]
+    d_boxes = [t.to(dev) for t in host_boxes]
+    d_scores = [t.to(dev) for t in host_scores]
+    pipe = pipeline.FramePipeline(geom, pfn, N_POINTS, device=dev)
+    pipe_given = pipeline.FramePipeline(geom, pfn, N_POINTS, order=_lib.ORDER_GIVEN, device=dev)
+    nms = pipeline.NmsStage(N_BOXES, device=dev)
+    canvases = [pipe.new_canvas() for _ in range(RING_CANVAS)]
+    stream = torch.cuda.current_stream()
+
+    def step(i, p=pipe):
+        j = i % RING_TILES
+        p.run(d_pts[j], canvases[i % RING_CANVAS], stream)
+        nms.run(d_boxes[j], d_scores[j], NMS_SCORE_THR, NMS_IOU_THR, 0, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    m_pillars = int(pipe.voxel_num.item())
+    keep_n = int(nms.count.item())
+
+    # ---- headline: device-resident, K steps ----------------------------------------------------
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
+    l0 = _lib.launch_count()
+    ms_total = timed(step, K)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+    value = world * K / (ms_total * 1e-3)
+
+    # ---- same, points pre-ordered (PP_ORDER_GIVEN: no reflectance sort) -------------------------
+    for i in range(3):
+        step(i, pipe_given)
+    ms_given = timed(lambda i: step(i, pipe_given), K)
+
+    # ---- stage split (events around each stage, separate pass) ---------------------------------
+    def split_pass(steps):
+        evs = []
+        barrier()
+        for i in range(steps):
+            j = i % RING_TILES
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record(stream)
+            pipe.voxelize(d_pts[j], stream)
+            e[1].record(stream)
+            pipe.encode_scatter(canvases[i % RING_CANVAS], stream)
+            e[2].record(stream)
+            nms.run(d_boxes[j], d_scores[j], NMS_SCORE_THR, NMS_IOU_THR, 0, stream)
+            e[3].record(stream)
+            evs.append(e)
+        torch.cuda.synchronize()
+        return [sum(e[k].elapsed_time(e[k + 1]) for e in evs) / steps for k in range(3)]
+
+    t_vox, t_enc, t_nms = split_pass(min(K, 50))
+
+    # ---- per-kernel durations with CUDA events on the launching stream (library profiler) --------
+    _lib.profile(True)
+    prof_steps = min(K, 50)
+    for i in range(prof_steps):
+        step(i)
+    torch.cuda.synchronize()
+    _lib.profile(False)
+    kern = {k: {"launches_per_step": c / prof_steps, "ms_per_step": ms / prof_steps, "avg_us": 1e3 * ms / c}
+            for k, (c, ms) in _lib.profile_report().items()}
+
+    # ---- e2e: host buffers in, host results out, through the same C ABI -------------------------
+    stage_pts = torch.empty_like(d_pts[0])
+    stage_boxes, stage_scores = torch.empty_like(d_boxes[0]), torch.empty_like(d_scores[0])
+    out_keep = torch.empty((N_BOXES,), dtype=torch.int64).pin_memory()
+    out_cnt = torch.empty((2,), dtype=torch.int32).pin_memory()
+    h2d = host_pts[0].numel() * 4 + host_boxes[0].numel() * 4 + host_scores[0].numel() * 4
+    d2h = out_keep.numel() * 8 + 8
+
+    def e2e_step(i):
+        j = i % RING_TILES
+        stage_pts.copy_(host_pts[j], non_blocking=True)
+        stage_boxes.copy_(host_boxes[j], non_blocking=True)
+        stage_scores.copy_(host_scores[j], non_blocking=True)
+        pipe.run(stage_pts, canvases[i % RING_CANVAS], stream)
+        nms.run(stage_boxes, stage_scores, NMS_SCORE_THR, NMS_IOU_THR, 0, stream)
+        out_keep.copy_(nms.keep, non_blocking=True)
+        out_cnt[0:1].copy_(nms.count, non_blocking=True)
+        out_cnt[1:2].copy_(pipe.voxel_num, non_blocking=True)
+        stream.synchronize()           # the caller gets its frame's results before the next frame
+
+    for i in range(3):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, K)
+    e2e_value = world * K / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = {}, "fallback"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_src = "measured"
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    vox_b, enc_b = pipe.algorithmic_bytes(N_POINTS, m_pillars)
+    # algorithmic bytes per launch of each kernel that moves boundary data (DESIGN.md "Kernels");
+    # sort / scan / rank kernels move only workspace traffic and have 0 algorithmic bytes
+    canvas_b = (pipe.U + 1) * pipe.D * pipe.H * pipe.W * 4
+    kbytes = {"scatter_canvas_kernel": canvas_b + m_pillars * (pipe.U + 1) * 4,
+              "vox_cell_kernel": N_POINTS * pipe.C * 4,
+              "vox_gather_kernel": m_pillars * pipe.P * pipe.C * 4 + m_pillars * 4,
+              "pfn_kernel": m_pillars * pipe.P * pipe.C * 4 + m_pillars * 16 + m_pillars * (pipe.U + 1) * 4}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    roofline = None
+    if dom:
+        per_launch_b = kbytes.get(dom, 0)
+        ach = per_launch_b / (kern[dom]["avg_us"] * 1e-6) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": per_launch_b, "avg_launch_us": kern[dom]["avg_us"],
+                    "share_of_step": kern[dom]["ms_per_step"] / max(sum(v["ms_per_step"] for v in kern.values()), 1e-9),
+                    "how": "CUDA events on the launching stream around every launch (pp_profile_*), separate pass of "
+                           "%d steps after the timed region" % prof_steps}
+    stage_roof = {
+        "voxelize": {"algorithmic_MB": vox_b / 1e6, "us": 1e3 * t_vox, "GBps": vox_b / (t_vox * 1e-3) / 1e9,
+                     "frac": vox_b / (t_vox * 1e-3) / 1e9 / hbm_peak},
+        "decorate_pfn_scatter": {"algorithmic_MB": enc_b / 1e6, "us": 1e3 * t_enc,
+                                 "GBps": enc_b / (t_enc * 1e-3) / 1e9, "frac": enc_b / (t_enc * 1e-3) / 1e9 / hbm_peak},
+        "voxelize+scatter": {"algorithmic_MB": (vox_b + enc_b) / 1e6, "us": 1e3 * (t_vox + t_enc),
+                             "frac": (vox_b + enc_b) / ((t_vox + t_enc) * 1e-3) / 1e9 / hbm_peak,
+                             "target_frac": 0.6},
+        "nms_20k": {"us": 1e3 * t_nms, "target_us": 1000.0, "kept": keep_n}}
+    cpu = cpu_baseline(args.cpu_seconds) if world == 1 else None
+    line = {"metric": "voxelize+scatter+NMS frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(base_config(world), pillars=m_pillars, nms_kept=keep_n),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / K,
+                    "note": "pinned host points/boxes/scores -> H2D -> same C-ABI calls -> D2H keep list + counts, "
+                            "stream synchronised every frame; the canvas stays on the device for the backbone"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "stages": stage_roof, "kernels": kern,
+            "given_order": {"value": world * K / (ms_given * 1e-3), "unit": "frames/s", "ms_per_step": ms_given / K,
+                            "note": "PP_ORDER_GIVEN: points already in processing order (no reflectance sort)"}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,11 @@ PP_API int pp_version(void);
 PP_API const char *pp_last_error(void);
 /* number of kernels this library has launched in this process (for gpu_launches accounting) */
 PP_API int64_t pp_launch_count(void);
+/* Opt-in per-kernel timing with CUDA events on the launching stream (used by bench.py for the roofline
+ * numbers).  pp_profile_enable(1) clears and starts collecting, (0) stops; pp_profile_report waits for
+ * the last event and writes one line per kernel: "<name> <launches> <total_ms>\n". */
+PP_API int pp_profile_enable(int on);
+PP_API int pp_profile_report(char *buf, size_t buf_bytes);
 
 /* ------------------------------------------------------------------------------------------
  * Stage 1 -- hard voxelization.

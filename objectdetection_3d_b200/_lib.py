@@ -32,6 +32,8 @@ SIGNATURES = {
     "pp_version": (ctypes.c_int, []),
     "pp_last_error": (ctypes.c_char_p, []),
     "pp_launch_count": (_i64, []),
+    "pp_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "pp_profile_report": (ctypes.c_int, [ctypes.c_char_p, _sz]),
     "pp_voxelize_max_rows": (_i64, [_i64, _cfgp]),
     "pp_voxelize_workspace_bytes": (_sz, [_i64, _cfgp, ctypes.c_int]),
     "pp_voxelize": (ctypes.c_int, [_vp, _i64, _cfgp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -94,3 +96,18 @@ def check(rc, invalid_exc=ValueError):
 
 def launch_count():
     return int(load().pp_launch_count())
+
+
+def profile(on):
+    load().pp_profile_enable(1 if on else 0)
+
+
+def profile_report():
+    """{kernel name: (launches, total_ms)} collected since profile(True)."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(load().pp_profile_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out[name] = (int(cnt), float(ms))
+    return out

@@ -156,6 +156,7 @@ using namespace pp;
 
 extern "C" int pp_box_encode(const float *src, const float *dst, int64_t K, float *out, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(K >= 0, "K < 0");
     if (K == 0) return PP_OK;
     PP_REQUIRE(src && dst && out, "null pointer");
@@ -165,6 +166,7 @@ extern "C" int pp_box_encode(const float *src, const float *dst, int64_t K, floa
 
 extern "C" int pp_box_decode(const float *anchors, const float *deltas, int64_t K, float *out, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(K >= 0, "K < 0");
     if (K == 0) return PP_OK;
     PP_REQUIRE(anchors && deltas && out, "null pointer");
@@ -174,6 +176,7 @@ extern "C" int pp_box_decode(const float *anchors, const float *deltas, int64_t 
 
 extern "C" int pp_limit_period(const float *val, int64_t n, float offset, float period, float *out, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(n >= 0, "n < 0");
     if (n == 0) return PP_OK;
     PP_REQUIRE(val && out, "null pointer");
@@ -184,6 +187,7 @@ extern "C" int pp_limit_period(const float *val, int64_t n, float offset, float 
 extern "C" int pp_grid_anchors(const float *range6_host, const float *sizes_host, int S, const float *rots_host, int R,
                                int D, int H, int W, float *out, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(range6_host && sizes_host && rots_host && out, "null pointer");
     PP_REQUIRE(S > 0 && S <= 16 && R > 0 && R <= 16, "1..16 sizes / rotations supported");
     PP_REQUIRE(D > 0 && H > 0 && W > 0, "bad feature map");
@@ -199,6 +203,7 @@ extern "C" int pp_grid_anchors(const float *range6_host, const float *sizes_host
 
 extern "C" int pp_box_corners3d(const float *boxes, int64_t N, float *corners, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(N >= 0, "N < 0");
     if (N == 0) return PP_OK;
     PP_REQUIRE(boxes && corners, "null pointer");
@@ -208,6 +213,7 @@ extern "C" int pp_box_corners3d(const float *boxes, int64_t N, float *corners, p
 
 extern "C" int pp_box_aabb2d(const float *boxes, int64_t N, float *rect, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(N >= 0, "N < 0");
     if (N == 0) return PP_OK;
     PP_REQUIRE(boxes && rect, "null pointer");
@@ -219,6 +225,7 @@ extern "C" int pp_box_aabb2d(const float *boxes, int64_t N, float *rect, pp_stre
 extern "C" int pp_bbox_iou2d(const float *b1, int64_t m, const float *b2, int64_t n, int mode, float eps, float *out,
                              pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(m >= 0 && n >= 0, "negative size");
     PP_REQUIRE(mode == PP_IOU || mode == PP_IOF || mode == PP_GIOU, "Unsupported mode");
     if (m == 0 || n == 0) return PP_OK;
@@ -233,6 +240,7 @@ extern "C" int pp_bbox_iou2d(const float *b1, int64_t m, const float *b2, int64_
 extern "C" int pp_iou_jit(const float *boxes, int64_t N, const float *query, int64_t K, double eps, float *out,
                           pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(N >= 0 && K >= 0, "negative size");
     if (N == 0 || K == 0) return PP_OK;
     PP_REQUIRE(boxes && query && out, "null pointer");

@@ -12,6 +12,8 @@ namespace pp {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+void prof_mark(const char *name);   // no-op unless pp_profile_enable(1)
+void enter(cudaStream_t st);        // call first in every launching entry point
 
 inline int check_launch(const char *what)
 {
@@ -21,6 +23,7 @@ inline int check_launch(const char *what)
         return PP_ERR_CUDA;
     }
     count_launch();
+    prof_mark(what);
     return PP_OK;
 }
 

@@ -186,6 +186,7 @@ extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_st
                       float iou_thr, int64_t *keep, int32_t *keep_count, void *workspace, size_t workspace_bytes,
                       pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     PP_REQUIRE(keep_count, "null keep_count");
     PP_REQUIRE(N >= 0 && N <= 131072, "N must be in [0, 131072]");
@@ -202,7 +203,7 @@ extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_st
         return PP_ERR_WORKSPACE;
     }
     PP_CUDA_TRY(cudaMemsetAsync(w.n_cand, 0, sizeof(int32_t), st));
-    count_launch();
+    prof_mark("memset");
     const unsigned nb = (unsigned)ceil_div(N, NMS_THREADS);
     nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.n_cand);
     if (int rc = check_launch("nms_prepare_kernel")) return rc;

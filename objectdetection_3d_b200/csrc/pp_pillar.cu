@@ -252,6 +252,7 @@ extern "C" int pp_decorate(const float *voxels, const void *num_points, int num_
                            int coors_kind, int64_t M, const int32_t *m_dev, int P, int C, float vx, float vy,
                            float x_off, float y_off, float *out, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(M >= 0 && P > 0 && C >= 3, "bad shape");
     if (M == 0) return PP_OK;
     PP_REQUIRE(voxels && num_points && coors && out, "null pointer");
@@ -288,6 +289,7 @@ static int launch_pfn(bool decorate, const PillarIn &a, const float *W, const fl
 extern "C" int pp_pfn_layer(const float *in, int64_t M, int P, int Cin, const float *weight, const float *scale,
                             const float *shift, int U, int last_layer, float *out, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(M >= 0 && P > 0 && Cin > 0 && U > 0, "bad shape");
     if (M == 0) return PP_OK;
     PP_REQUIRE(in && weight && scale && shift && out, "null pointer");
@@ -301,6 +303,7 @@ extern "C" int pp_pillar_features(const float *voxels, const void *num_points, i
                                   float x_off, float y_off, const float *weight, const float *scale,
                                   const float *shift, int U, float *feat, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(M >= 0 && P > 0 && C >= 3 && U > 0, "bad shape");
     if (M == 0) return PP_OK;
     PP_REQUIRE(voxels && num_points && coors && weight && scale && shift && feat, "null pointer");
@@ -322,6 +325,7 @@ extern "C" int pp_scatter_dense(const float *feat, const void *coors, int coors_
                                 int C, int batch_index, int B, int D, int H, int W, float *canvas, void *map_ws,
                                 size_t map_ws_bytes, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     PP_REQUIRE(M >= 0 && C > 0 && B > 0 && D > 0 && H > 0 && W > 0, "bad shape");
     PP_REQUIRE(canvas && map_ws, "null pointer");
@@ -336,7 +340,7 @@ extern "C" int pp_scatter_dense(const float *feat, const void *coors, int coors_
     PP_REQUIRE((int64_t)B * D * tiles_per_plane < (1ll << 31), "canvas too large");
     int32_t *map = (int32_t *)map_ws;
     PP_CUDA_TRY(cudaMemsetAsync(map, 0xFF, need, st));
-    count_launch();
+    prof_mark("memset");
     if (M > 0) {
         PP_REQUIRE(feat && coors, "null pointer");
         CoorsIn c{coors, coors_kind, batch_index};

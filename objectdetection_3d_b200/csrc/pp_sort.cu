@@ -179,6 +179,7 @@ int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *k
         return PP_ERR_WORKSPACE;
     }
     PP_CUDA_TRY(cudaMemsetAsync(ws, 0, s.zero_bytes, st));
+    prof_mark("memset");
     int hist_blocks = (int)(ceil_div(n, SORT_THREADS * 16) < 148 * 4 ? ceil_div(n, SORT_THREADS * 16) : 148 * 4);
     sort_hist_kernel<<<hist_blocks, SORT_THREADS, 0, st>>>(keys_in, n, s.hist);
     if (int rc = check_launch("sort_hist_kernel")) return rc;
@@ -203,6 +204,7 @@ extern "C" int pp_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_i
                                  uint32_t *vals_out, int64_t n, void *workspace, size_t workspace_bytes,
                                  pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     PP_REQUIRE(n >= 0, "n < 0");
     if (n == 0) return PP_OK;
     PP_REQUIRE(keys_in && keys_out && vals_out && workspace, "null pointer");

@@ -305,6 +305,7 @@ extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *c
                            float *voxels, int32_t *coors, int32_t *num_points, int32_t *voxel_num,
                            int32_t *pillar_map, void *workspace, size_t workspace_bytes, pp_stream_t stream)
 {
+    pp::enter((cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     PP_REQUIRE(cfg && voxel_num, "null cfg / voxel_num");
     PP_REQUIRE(n >= 0 && n < (1ll << 30), "n_points out of range");
@@ -348,7 +349,7 @@ extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *c
     PP_CUDA_TRY(cudaMemsetAsync(workspace, 0x7F, w.fill7f_bytes, st));
     PP_CUDA_TRY(cudaMemsetAsync((char *)workspace + w.zero_off, 0, w.zero_bytes, st));
     if (pillar_map) PP_CUDA_TRY(cudaMemsetAsync(pillar_map, 0xFF, (size_t)cells * 4, st));
-    count_launch(pillar_map ? 3 : 2);
+    prof_mark("memset");
 
     const int32_t *order_perm = nullptr;
     if (order == PP_ORDER_PERM) {
