@@ -15,7 +15,7 @@ namespace {
 
 typedef unsigned long long u64;
 constexpr int NMS_THREADS = 256;
-constexpr int SWEEP_THREADS = 512;
+constexpr int SWEEP_THREADS = 1024;
 
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, int64_t stride, int64_t N,
@@ -46,94 +46,133 @@ nms_gather_kernel(const float4 *__restrict__ rect, const uint32_t *__restrict__ 
     if (r < *n_cand) srect[r] = rect[order[r]];
 }
 
-__global__ void __launch_bounds__(64)
+constexpr int MT_ROWS = 128;   // rows (selected boxes) per CTA, one per thread
+constexpr int MT_COLS = 256;   // columns (remaining boxes) per CTA = 4 mask words
+
+// bit j of mask[i][w] = (64w + j > i) && iou(box_{64w+j}, box_i) > thr.  Words entirely on or below the
+// diagonal are never read by the sweep and are not written.
+__global__ void __launch_bounds__(MT_ROWS)
 nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_cand, float thr, int nw_stride,
                 u64 *__restrict__ mask)
 {
     const int n = *n_cand;
-    const int rb = blockIdx.y, cb = blockIdx.x;
-    if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
-    __shared__ float4 s_col[64];
+    const int row0 = blockIdx.y * MT_ROWS, col0 = blockIdx.x * MT_COLS;
+    if (row0 >= n || col0 >= n || col0 + MT_COLS <= row0) return;
+    __shared__ float4 s_col[MT_COLS];
     const int t = threadIdx.x;
-    const int col = cb * 64 + t;
-    if (col < n) s_col[t] = srect[col];
+#pragma unroll
+    for (int k = 0; k < MT_COLS / MT_ROWS; ++k) {
+        const int c = col0 + t + k * MT_ROWS;
+        // out-of-range columns get an empty rectangle: never intersects
+        s_col[t + k * MT_ROWS] = c < n ? srect[c] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+    }
     __syncthreads();
-    const int i = rb * 64 + t;
+    const int i = row0 + t;
     if (i >= n) return;
     const float4 a = srect[i];
-    const int jmax = min(64, n - cb * 64);
     const bool zero_hits = 0.f > thr;        // iou == 0 still "exceeds" a negative threshold
-    u64 bits = 0;
-    for (int j = (rb == cb) ? t + 1 : 0; j < jmax; ++j) {
-        const float4 q = s_col[j];
-        // fast reject: empty intersection -> overlap == 0 -> iou == 0 exactly
-        const float w = __fsub_rn(fminf(q.z, a.z), fmaxf(q.x, a.x));
-        const float h = __fsub_rn(fminf(q.w, a.w), fmaxf(q.y, a.y));
-        bool hit;
-        if (w <= 0.f || h <= 0.f) hit = zero_hits;
-        else hit = rect_iou(q, a, 0, 1e-6f) > thr;      // (remaining, selected) order of :412
-        if (hit) bits |= 1ull << j;
+#pragma unroll 1
+    for (int wd = 0; wd < MT_COLS / 64; ++wd) {
+        const int c_start = col0 + wd * 64;
+        if (c_start >= n) break;
+        if (c_start + 63 < i) continue;       // entirely below the diagonal: never read
+        u64 bits = 0;
+#pragma unroll 8
+        for (int j = 0; j < 64; ++j) {
+            const float4 q = s_col[wd * 64 + j];
+            // fast reject: empty intersection -> overlap == 0 -> iou == 0 exactly
+            const float w = __fsub_rn(fminf(q.z, a.z), fmaxf(q.x, a.x));
+            const float h = __fsub_rn(fminf(q.w, a.w), fmaxf(q.y, a.y));
+            bool hit = zero_hits;
+            if (w > 0.f && h > 0.f) hit = rect_iou(q, a, 0, 1e-6f) > thr;   // (remaining, selected) order of :412
+            bits |= (u64)hit << j;
+        }
+        if (c_start <= i) bits &= ~((2ull << (i - c_start)) - 1ull);      // keep only columns > i
+        if (c_start + 64 > n) bits &= (1ull << (n - c_start)) - 1ull;     // and columns < n
+        mask[(size_t)i * nw_stride + (c_start >> 6)] = bits;
     }
-    mask[(size_t)i * nw_stride + cb] = bits;
 }
 
+// Sweep: warp 0 ("resolver") walks the 64-box blocks in rank order.  For block cb it takes the final
+// removed word, keeps the surviving boxes with a find-first-set chain over the prefetched diagonal word
+// (one iteration per KEPT box), and ORs the kept rows' next word (cb+1) itself.  The other 31 warps
+// ("spreaders") run one block behind and OR the kept rows of block cb-1 into the words >= cb+1, so their
+// L2 latency overlaps the resolver's chain.  One CTA barrier per block.
 __global__ void __launch_bounds__(SWEEP_THREADS)
 nms_sweep_kernel(const u64 *__restrict__ mask, int nw_stride, const int32_t *__restrict__ n_cand,
                  const uint32_t *__restrict__ order, int64_t *__restrict__ keep, int32_t *__restrict__ keep_count)
 {
     extern __shared__ u64 removed[];
-    __shared__ u64 s_kept;
+    __shared__ u64 s_kept[2];
     const int n = *n_cand;
     const int nw = (n + 63) >> 6;
     const int tid = threadIdx.x, lane = tid & 31;
     for (int w = tid; w < nw; w += SWEEP_THREADS) removed[w] = 0;
+    if (tid < 2) s_kept[tid] = 0;
     __syncthreads();
     int kept_total = 0;
-    u64 d0 = 0, d1 = 0;
-    if (tid < 32 && nw > 0) {
-        d0 = (lane < n) ? mask[(size_t)lane * nw_stride] : 0;
-        d1 = (32 + lane < n) ? mask[(size_t)(32 + lane) * nw_stride] : 0;
-    }
-    for (int cb = 0; cb < nw; ++cb) {
-        if (tid < 32) {
-            const int valid = min(64, n - cb * 64);
-            u64 alive = ~removed[cb];
-            if (valid < 64) alive &= (1ull << valid) - 1;
-            u64 kept = 0;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                const u64 di = __shfl_sync(0xFFFFFFFFu, i < 32 ? d0 : d1, i & 31);
-                if ((alive >> i) & 1ull) {
-                    kept |= 1ull << i;
-                    alive &= ~di;
-                }
-            }
-            if (lane == 0) s_kept = kept;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int bit = lane + 32 * h;
-                if ((kept >> bit) & 1ull)
-                    keep[kept_total + __popcll(kept & ((1ull << bit) - 1))] = (int64_t)order[cb * 64 + bit];
-            }
-            kept_total += __popcll(kept);
-            // prefetch the next diagonal block while the other warps OR the kept rows
-            if (cb + 1 < nw) {
-                const int r0 = (cb + 1) * 64 + lane, r1 = r0 + 32;
-                d0 = (r0 < n) ? mask[(size_t)r0 * nw_stride + cb + 1] : 0;
-                d1 = (r1 < n) ? mask[(size_t)r1 * nw_stride + cb + 1] : 0;
+    // band[k] = {diag lo, diag hi, next lo, next hi} of block cb + k, prefetched two blocks ahead
+    u64 band[3][4];
+    auto load_band = [&](int b, u64 (&d)[4]) {
+        d[0] = d[1] = d[2] = d[3] = 0;
+        if (b < nw) {
+            const int r0 = b * 64 + lane, r1 = r0 + 32;
+            if (r0 < n) d[0] = mask[(size_t)r0 * nw_stride + b];
+            if (r1 < n) d[1] = mask[(size_t)r1 * nw_stride + b];
+            if (b + 1 < nw) {
+                if (r0 < n) d[2] = mask[(size_t)r0 * nw_stride + b + 1];
+                if (r1 < n) d[3] = mask[(size_t)r1 * nw_stride + b + 1];
             }
         }
-        __syncthreads();
-        const u64 kept = s_kept;
-        if (kept) {
-            for (int w = cb + 1 + tid; w < nw; w += SWEEP_THREADS) {
-                u64 acc = 0, k = kept;
-                while (k) {
-                    const int i = __ffsll((long long)k) - 1;
-                    k &= k - 1;
-                    acc |= mask[(size_t)(cb * 64 + i) * nw_stride + w];
+    };
+    if (tid < 32) {
+        load_band(0, band[0]);
+        load_band(1, band[1]);
+    }
+    for (int cb = 0; cb <= nw; ++cb) {
+        if (tid < 32) {
+            if (cb < nw) {
+                load_band(cb + 2, band[2]);
+                const int valid = min(64, n - cb * 64);
+                u64 alive = ~removed[cb];
+                if (valid < 64) alive &= (1ull << valid) - 1;
+                u64 kept = 0;
+                while (alive) {
+                    const int i = __ffsll((long long)alive) - 1;
+                    kept |= 1ull << i;
+                    const u64 di = __shfl_sync(0xFFFFFFFFu, i < 32 ? band[0][0] : band[0][1], i & 31);
+                    alive &= ~(di | (1ull << i));
                 }
-                removed[w] |= acc;
+                if (lane == 0) s_kept[cb & 1] = kept;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int bit = lane + 32 * h;
+                    if ((kept >> bit) & 1ull)
+                        keep[kept_total + __popcll(kept & ((1ull << bit) - 1))] = (int64_t)order[cb * 64 + bit];
+                }
+                kept_total += __popcll(kept);
+                // the kept rows' word cb+1 must be final before the next block is resolved
+                u64 nx = (((kept >> lane) & 1ull) ? band[0][2] : 0ull) | (((kept >> (lane + 32)) & 1ull) ? band[0][3] : 0ull);
+                const unsigned lo = __reduce_or_sync(0xFFFFFFFFu, (unsigned)nx);
+                const unsigned hi = __reduce_or_sync(0xFFFFFFFFu, (unsigned)(nx >> 32));
+                if (lane == 0 && cb + 1 < nw && (lo | hi)) atomicOr(&removed[cb + 1], ((u64)hi << 32) | lo);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { band[0][k] = band[1][k]; band[1][k] = band[2][k]; }
+            }
+        } else if (cb >= 1) {
+            // spreaders: block cb-1 -> words >= cb+1
+            const int pb = cb - 1;
+            const u64 kept = s_kept[pb & 1];
+            if (kept) {
+                for (int w = cb + 1 + (tid - 32); w < nw; w += SWEEP_THREADS - 32) {
+                    u64 acc = 0, k = kept;
+                    while (k) {
+                        const int i = __ffsll((long long)k) - 1;
+                        k &= k - 1;
+                        acc |= mask[(size_t)(pb * 64 + i) * nw_stride + w];
+                    }
+                    if (acc) atomicOr(&removed[w], acc);
+                }
             }
         }
         __syncthreads();
@@ -210,8 +249,8 @@ extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_st
     if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st)) return rc;
     nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.n_cand, w.srect);
     if (int rc = check_launch("nms_gather_kernel")) return rc;
-    dim3 grid(w.nw, w.nw);
-    nms_mask_kernel<<<grid, 64, 0, st>>>(w.srect, w.n_cand, iou_thr, w.nw, w.mask);
+    dim3 grid((unsigned)ceil_div(N, MT_COLS), (unsigned)ceil_div(N, MT_ROWS));
+    nms_mask_kernel<<<grid, MT_ROWS, 0, st>>>(w.srect, w.n_cand, iou_thr, w.nw, w.mask);
     if (int rc = check_launch("nms_mask_kernel")) return rc;
     size_t smem = (size_t)w.nw * sizeof(u64);
     nms_sweep_kernel<<<1, SWEEP_THREADS, smem, st>>>(w.mask, w.nw, w.n_cand, w.order, keep, keep_count);

@@ -82,7 +82,7 @@ __device__ void decorate_row(const PillarIn &a, int64_t m, int n, float *row, in
 
 __global__ void __launch_bounds__(PIL_THREADS) decorate_kernel(const PillarIn a, float *__restrict__ out)
 {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int CO = a.C + 5, ld = CO | 1;
     float *row = smem + warp * a.P * ld;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(PIL_THREADS)
 pfn_kernel(const PillarIn a, const float *__restrict__ W, const float *__restrict__ scale,
            const float *__restrict__ shift, int U, int last_layer, int append_num, float *__restrict__ out)
 {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int P = a.P, Cin = a.Cin;
     const int ldw = Cin | 1, ldi = Cin | 1;
@@ -150,6 +150,63 @@ pfn_kernel(const PillarIn a, const float *__restrict__ W, const float *__restric
             }
         }
         if (last_layer && append_num && lane == 0) out[m * out_w + U] = (float)n;   // :526
+        __syncwarp();
+    }
+}
+
+// Fast path of the fused single-layer PillarFeatureNet (Cin <= 12, U <= 64): the two weight rows a lane
+// owns live in registers for the whole grid-stride loop, the decorated row is read back as broadcast
+// 128-bit shared loads.  Same arithmetic order as pfn_kernel (bit-identical results).
+constexpr int PFN_LDI = 12;
+__global__ void __launch_bounds__(PIL_THREADS)
+pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const float *__restrict__ scale,
+                       const float *__restrict__ shift, int U, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int P = a.P, Cin = a.Cin;
+    float *row = smem + warp * P * PFN_LDI;
+    float w0[PFN_LDI], w1[PFN_LDI];
+    const int u0 = lane, u1 = lane + 32;
+#pragma unroll
+    for (int k = 0; k < PFN_LDI; ++k) {
+        w0[k] = (u0 < U && k < Cin) ? W[u0 * Cin + k] : 0.f;
+        w1[k] = (u1 < U && k < Cin) ? W[u1 * Cin + k] : 0.f;
+    }
+    const float sc0 = u0 < U ? scale[u0] : 0.f, sh0 = u0 < U ? shift[u0] : 0.f;
+    const float sc1 = u1 < U ? scale[u1] : 0.f, sh1 = u1 < U ? shift[u1] : 0.f;
+    int64_t M = a.M;
+    if (a.m_dev) { int64_t md = *a.m_dev; M = md < M ? md : M; }
+    const int out_w = U + 1;
+    for (int64_t m = (int64_t)blockIdx.x * PIL_WARPS + warp; m < M; m += (int64_t)gridDim.x * PIL_WARPS) {
+        const int n = load_num(a, m);
+        decorate_row(a, m, n, row, PFN_LDI, lane);
+        __syncwarp();
+        const int p_end = n < P ? n : P;
+        // zero-padded slots take part in the max (:403-410): they contribute relu(shift)
+        float mx0 = (p_end < P) ? fmaxf(sh0, 0.f) : -CUDART_INF_F;
+        float mx1 = (p_end < P) ? fmaxf(sh1, 0.f) : -CUDART_INF_F;
+        for (int p = 0; p < p_end; ++p) {
+            const float4 *f4 = reinterpret_cast<const float4 *>(row + p * PFN_LDI);
+            const float4 fa = f4[0], fb = f4[1], fc = f4[2];
+            const float f[PFN_LDI] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w, fc.x, fc.y, fc.z, fc.w};
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < PFN_LDI; ++k) {
+                if (k < Cin) {
+                    acc0 = __fadd_rn(acc0, __fmul_rn(f[k], w0[k]));
+                    acc1 = __fadd_rn(acc1, __fmul_rn(f[k], w1[k]));
+                }
+            }
+            float y0 = __fadd_rn(__fmul_rn(acc0, sc0), sh0);
+            float y1 = __fadd_rn(__fmul_rn(acc1, sc1), sh1);
+            mx0 = fmaxf(mx0, y0 > 0.f ? y0 : 0.f);
+            mx1 = fmaxf(mx1, y1 > 0.f ? y1 : 0.f);
+        }
+        float *o = out + m * out_w;
+        if (u0 < U) o[u0] = mx0;
+        if (u1 < U) o[u1] = mx1;
+        if (lane == 0) o[U] = (float)n;                                       // :526
         __syncwarp();
     }
 }
@@ -312,6 +369,12 @@ extern "C" int pp_pillar_features(const float *voxels, const void *num_points, i
     PillarIn a;
     fill_pillar_in(a, voxels, nullptr, num_points, num_kind, coors, coors_kind, M, m_dev, P, C, C + 5, vx, vy, x_off,
                    y_off);
+    if (C + 5 <= PFN_LDI && U <= 64) {
+        size_t smem = (size_t)PIL_WARPS * P * PFN_LDI * sizeof(float);
+        PP_REQUIRE(smem <= 48 * 1024, "P too large for the fused PFN kernel");
+        pfn_fused_small_kernel<<<pillar_grid(M), PIL_THREADS, smem, (cudaStream_t)stream>>>(a, weight, scale, shift, U, feat);
+        return check_launch("pfn_fused_small_kernel");
+    }
     return launch_pfn(true, a, weight, scale, shift, U, 1, 1, feat, (cudaStream_t)stream);
 }
 
