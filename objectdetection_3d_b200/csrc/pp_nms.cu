@@ -46,14 +46,22 @@ nms_gather_kernel(const float4 *__restrict__ rect, const uint32_t *__restrict__ 
     if (r < *n_cand) srect[r] = rect[order[r]];
 }
 
+constexpr int SW_L = 7;                     // words after the diagonal handled by the sweep's resolver warp
+constexpr int SW_RING = 8;                  // band blocks in flight in the sweep
+constexpr int SW_BAND = (SW_L + 1) * 64;    // u64 per band block: band[b][k][row] = mask[64b + row][b + k]
+
 constexpr int MT_ROWS = 128;   // rows (selected boxes) per CTA, one per thread
 constexpr int MT_COLS = 256;   // columns (remaining boxes) per CTA = 4 mask words
 
-// bit j of mask[i][w] = (64w + j > i) && iou(box_{64w+j}, box_i) > thr.  Words entirely on or below the
+// bit j of mask[i][w] = (64w + j > i) && iou(box_{64w+j}, box_i) > thr.  Words entirely below the
 // diagonal are never read by the sweep and are not written.
+// Two phases per 64-column word: (1) a 4-compare interval test marks the columns whose rectangle
+// intersects the row's (a superset of the hits when thr >= 0); (2) only those columns get the exact
+// bbox_iou2D evaluation (rect_iou, IEEE division), so decisions equal the reference's `iou > thr`.
+template <bool PREFILTER>
 __global__ void __launch_bounds__(MT_ROWS)
 nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_cand, float thr, int nw_stride,
-                u64 *__restrict__ mask)
+                u64 *__restrict__ mask, u64 *__restrict__ band)
 {
     const int n = *n_cand;
     const int row0 = blockIdx.y * MT_ROWS, col0 = blockIdx.x * MT_COLS;
@@ -70,118 +78,214 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
     const int i = row0 + t;
     if (i >= n) return;
     const float4 a = srect[i];
-    const bool zero_hits = 0.f > thr;        // iou == 0 still "exceeds" a negative threshold
 #pragma unroll 1
     for (int wd = 0; wd < MT_COLS / 64; ++wd) {
         const int c_start = col0 + wd * 64;
         if (c_start >= n) break;
         if (c_start + 63 < i) continue;       // entirely below the diagonal: never read
-        u64 bits = 0;
-#pragma unroll 8
-        for (int j = 0; j < 64; ++j) {
-            const float4 q = s_col[wd * 64 + j];
-            // fast reject: empty intersection -> overlap == 0 -> iou == 0 exactly
-            const float w = __fsub_rn(fminf(q.z, a.z), fmaxf(q.x, a.x));
-            const float h = __fsub_rn(fminf(q.w, a.w), fmaxf(q.y, a.y));
-            bool hit = zero_hits;
-            if (w > 0.f && h > 0.f) hit = rect_iou(q, a, 0, 1e-6f) > thr;   // (remaining, selected) order of :412
-            bits |= (u64)hit << j;
+        unsigned lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
+        if (PREFILTER) {
+            lo = hi = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float4 q = s_col[wd * 64 + j];
+                if (q.z > a.x && a.z > q.x && q.w > a.y && a.w > q.y) lo |= 1u << j;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float4 q = s_col[wd * 64 + 32 + j];
+                if (q.z > a.x && a.z > q.x && q.w > a.y && a.w > q.y) hi |= 1u << j;
+            }
         }
-        if (c_start <= i) bits &= ~((2ull << (i - c_start)) - 1ull);      // keep only columns > i
-        if (c_start + 64 > n) bits &= (1ull << (n - c_start)) - 1ull;     // and columns < n
-        mask[(size_t)i * nw_stride + (c_start >> 6)] = bits;
+        u64 cand = ((u64)hi << 32) | lo;
+        if (c_start <= i) cand &= ~((2ull << (i - c_start)) - 1ull);      // keep only columns > i
+        if (c_start + 64 > n) cand &= (1ull << (n - c_start)) - 1ull;     // and columns < n
+        u64 bits = 0;
+        while (cand) {
+            const int j = __ffsll((long long)cand) - 1;
+            cand &= cand - 1;
+            // (remaining, selected) argument order of model/utils.py:412
+            if (rect_iou(s_col[wd * 64 + j], a, 0, 1e-6f) > thr) bits |= 1ull << j;
+        }
+        const int cw = c_start >> 6, kb = cw - (i >> 6);
+        mask[(size_t)i * nw_stride + cw] = bits;
+        // tile-major copy of the diagonal band, streamed by the sweep with one bulk copy per block
+        if (kb <= SW_L) band[((size_t)(i >> 6) * (SW_L + 1) + kb) * 64 + (i & 63)] = bits;
     }
 }
 
-// Sweep: warp 0 ("resolver") walks the 64-box blocks in rank order.  For block cb it takes the final
-// removed word, keeps the surviving boxes with a find-first-set chain over the prefetched diagonal word
-// (one iteration per KEPT box), and ORs the kept rows' next word (cb+1) itself.  The other 31 warps
-// ("spreaders") run one block behind and OR the kept rows of block cb-1 into the words >= cb+1, so their
-// L2 latency overlaps the resolver's chain.  One CTA barrier per block.
+// ---- sweep -------------------------------------------------------------------------------------
+// One CTA.  Warp 31 ("resolver") walks the 64-box blocks in rank order: it takes the final removed word of
+// block b, keeps the surviving boxes with a find-first-set chain over the diagonal word (one iteration per
+// KEPT box) and ORs the kept rows' next SW_L words itself, from a band of the mask that it streams into a
+// shared-memory ring with cp.async SW_RING blocks ahead.  The other 31 warps ("owners") each own mask words
+// w and accumulate the kept rows of all blocks <= w - SW_L - 1 as those blocks get resolved, so their L2
+// latency is hidden behind SW_L resolver steps.  Synchronisation is through shared-memory counters only.
+
+// acquire/release fence at CTA scope (MEMBAR.ALL.CTA): cheaper than __threadfence_block()'s fence.sc
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
 __global__ void __launch_bounds__(SWEEP_THREADS)
-nms_sweep_kernel(const u64 *__restrict__ mask, int nw_stride, const int32_t *__restrict__ n_cand,
-                 const uint32_t *__restrict__ order, int64_t *__restrict__ keep, int32_t *__restrict__ keep_count)
+nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int nw_stride,
+                 const int32_t *__restrict__ n_cand, const uint32_t *__restrict__ order, int64_t *__restrict__ keep,
+                 int32_t *__restrict__ keep_count, int nw_cap)
 {
-    extern __shared__ u64 removed[];
-    __shared__ u64 s_kept[2];
+    extern __shared__ __align__(16) u64 sw_smem[];
+    u64 *ring = sw_smem;                                   // [SW_RING][SW_L+1][64]
+    u64 *removed = ring + SW_RING * SW_BAND;               // [nw_cap]
+    u64 *kept_arr = removed + nw_cap;                      // [nw_cap]
+    u64 *removed_r = kept_arr + nw_cap;                    // [nw_cap] resolver-side contributions (no atomics)
+    volatile int *ready = (volatile int *)(removed_r + nw_cap);  // [nw_cap]
+    __shared__ volatile int s_resolved;
+    __shared__ __align__(8) u64 s_mbar[SW_RING];
     const int n = *n_cand;
     const int nw = (n + 63) >> 6;
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int w = tid; w < nw; w += SWEEP_THREADS) removed[w] = 0;
-    if (tid < 2) s_kept[tid] = 0;
-    __syncthreads();
-    int kept_total = 0;
-    // band[k] = {diag lo, diag hi, next lo, next hi} of block cb + k, prefetched two blocks ahead
-    u64 band[3][4];
-    auto load_band = [&](int b, u64 (&d)[4]) {
-        d[0] = d[1] = d[2] = d[3] = 0;
-        if (b < nw) {
-            const int r0 = b * 64 + lane, r1 = r0 + 32;
-            if (r0 < n) d[0] = mask[(size_t)r0 * nw_stride + b];
-            if (r1 < n) d[1] = mask[(size_t)r1 * nw_stride + b];
-            if (b + 1 < nw) {
-                if (r0 < n) d[2] = mask[(size_t)r0 * nw_stride + b + 1];
-                if (r1 < n) d[3] = mask[(size_t)r1 * nw_stride + b + 1];
-            }
-        }
-    };
-    if (tid < 32) {
-        load_band(0, band[0]);
-        load_band(1, band[1]);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int w = tid; w < nw; w += SWEEP_THREADS) { removed[w] = 0; removed_r[w] = 0; ready[w] = 0; }
+    if (tid == 0) {
+        s_resolved = 0;
+        for (int r = 0; r < SW_RING; ++r)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar[r])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (int cb = 0; cb <= nw; ++cb) {
-        if (tid < 32) {
-            if (cb < nw) {
-                load_band(cb + 2, band[2]);
-                const int valid = min(64, n - cb * 64);
-                u64 alive = ~removed[cb];
-                if (valid < 64) alive &= (1ull << valid) - 1;
-                u64 kept = 0;
-                while (alive) {
-                    const int i = __ffsll((long long)alive) - 1;
-                    kept |= 1ull << i;
-                    const u64 di = __shfl_sync(0xFFFFFFFFu, i < 32 ? band[0][0] : band[0][1], i & 31);
-                    alive &= ~(di | (1ull << i));
-                }
-                if (lane == 0) s_kept[cb & 1] = kept;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int bit = lane + 32 * h;
-                    if ((kept >> bit) & 1ull)
-                        keep[kept_total + __popcll(kept & ((1ull << bit) - 1))] = (int64_t)order[cb * 64 + bit];
-                }
-                kept_total += __popcll(kept);
-                // the kept rows' word cb+1 must be final before the next block is resolved
-                u64 nx = (((kept >> lane) & 1ull) ? band[0][2] : 0ull) | (((kept >> (lane + 32)) & 1ull) ? band[0][3] : 0ull);
-                const unsigned lo = __reduce_or_sync(0xFFFFFFFFu, (unsigned)nx);
-                const unsigned hi = __reduce_or_sync(0xFFFFFFFFu, (unsigned)(nx >> 32));
-                if (lane == 0 && cb + 1 < nw && (lo | hi)) atomicOr(&removed[cb + 1], ((u64)hi << 32) | lo);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { band[0][k] = band[1][k]; band[1][k] = band[2][k]; }
+    __syncthreads();
+
+    if (warp == SWEEP_THREADS / 32 - 1) {
+        // ------------------------------------------------------------------ resolver
+        // band of block b (4 KB, contiguous) -> ring slot b % SW_RING with one TMA bulk copy, SW_RING-1 ahead
+        auto issue_band = [&](int b) {
+            if (b < nw && lane == 0) {
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar[b % SW_RING]);
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (b % SW_RING) * SW_BAND);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(SW_BAND * 8) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(band + (size_t)b * SW_BAND), "r"(SW_BAND * 8), "r"(bar) : "memory");
             }
-        } else if (cb >= 1) {
-            // spreaders: block cb-1 -> words >= cb+1
-            const int pb = cb - 1;
-            const u64 kept = s_kept[pb & 1];
-            if (kept) {
-                for (int w = cb + 1 + (tid - 32); w < nw; w += SWEEP_THREADS - 32) {
-                    u64 acc = 0, k = kept;
-                    while (k) {
+        };
+        for (int b = 0; b < SW_RING - 1; ++b) issue_band(b);
+        for (int b = 0; b < nw; ++b) {
+            issue_band(b + SW_RING - 1);          // its slot was consumed in step b - 1
+            {
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar[b % SW_RING]);
+                const unsigned parity = (b / SW_RING) & 1;
+                unsigned ok;
+                do {
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                } while (!ok);
+            }
+            const u64 *slot = ring + (b % SW_RING) * SW_BAND;
+            if (b > SW_L) {
+                while (ready[b] == 0) { }      // pure spin: __nanosleep granularity (~1 us) would dominate the step
+            }
+            fence_cta();
+            const int valid = min(64, n - b * 64);
+            u64 alive = ~(*(volatile u64 *)(removed + b) | *(volatile u64 *)(removed_r + b));
+            if (valid < 64) alive &= (1ull << valid) - 1;
+            u64 kept = 0;
+            while (alive) {
+                const int i = __ffsll((long long)alive) - 1;
+                kept |= 1ull << i;
+                alive &= ~(slot[i] | (1ull << i));
+            }
+            if (lane == 0) {
+                kept_arr[b] = kept;
+                fence_cta();
+                s_resolved = b + 1;
+            }
+            // lanes 1..SW_L each own one of the next words: OR the kept rows' band words (shared memory)
+            if (kept && lane >= 1 && lane <= SW_L && b + lane < nw) {
+                u64 v = 0, k = kept;
+                while (k) {
+                    const int i = __ffsll((long long)k) - 1;
+                    k &= k - 1;
+                    v |= slot[lane * 64 + i];
+                }
+                if (v) *(volatile u64 *)(removed_r + b + lane) |= v;   // one lane per word per step
+            }
+            __syncwarp();      // orders the lanes' shared-memory traffic; the slot may be refilled next step
+        }
+    } else {
+        // ------------------------------------------------------------------ owners
+        const int n_owner = SWEEP_THREADS - 32;
+        for (int w = tid; w < nw; w += n_owner) {
+            const int last = w - SW_L - 1;      // blocks 0..last reach word w through this thread
+            u64 acc = 0, k = 0;
+            int b = 0, hi = -1;
+            bool have = false;                  // k holds the not yet consumed kept bits of block b
+            while (true) {
+                if (!have) {
+                    if (b > last) break;
+                    const int res = s_resolved;
+                    if (res <= b) continue;
+                    fence_cta();
+                    hi = min(res - 1, last);
+                    k = *(volatile u64 *)(kept_arr + b);
+                    have = true;
+                }
+                // gather up to 8 kept rows of the resolved blocks, then issue their loads back to back: an
+                // in-order warp stalls at the first use, so loads ORed one by one would serialise the L2 latency
+                long long off[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    while (k == 0 && b < hi) { ++b; k = *(volatile u64 *)(kept_arr + b); }
+                    off[j] = -1;
+                    if (k) {
                         const int i = __ffsll((long long)k) - 1;
                         k &= k - 1;
-                        acc |= mask[(size_t)(pb * 64 + i) * nw_stride + w];
+                        off[j] = (long long)(b * 64 + i) * nw_stride + w;
                     }
-                    if (acc) atomicOr(&removed[w], acc);
                 }
+                u64 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? mask[off[j]] : 0ull;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc |= v[j];
+                if (k == 0 && b >= hi) { have = false; b = hi + 1; }
             }
+            if (acc) atomicOr(removed + w, acc);
+            fence_cta();
+            ready[w] = 1;
+        }
+    }
+    // ---- expand the kept bitmaps to original indices, in rank order (all threads) -------------------
+    __syncthreads();
+    __shared__ int s_warp_sum[SWEEP_THREADS / 32];
+    __shared__ int s_base;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int w0 = 0; w0 < nw; w0 += SWEEP_THREADS) {
+        const int w = w0 + tid;
+        const u64 kept = w < nw ? kept_arr[w] : 0ull;
+        const int cnt = __popcll(kept);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp_sum[warp] = incl;
+        __syncthreads();
+        int pos = s_base + incl - cnt;
+        for (int q = 0; q < warp; ++q) pos += s_warp_sum[q];
+        u64 k = kept;
+        while (k) {
+            const int i = __ffsll((long long)k) - 1;
+            k &= k - 1;
+            keep[pos++] = (int64_t)order[w * 64 + i];
         }
         __syncthreads();
+        if (tid == SWEEP_THREADS - 1) s_base = pos;      // last thread holds the running total
+        __syncthreads();
     }
-    if (tid == 0) *keep_count = kept_total;
+    if (tid == 0) *keep_count = s_base;
 }
 
 struct NmsWs {
     int32_t *n_cand;
+    u64 *band;
+    size_t zero_bytes;
     float4 *rect, *srect;
     uint32_t *keys, *keys_sorted, *order;
     u64 *mask;
@@ -197,6 +301,8 @@ NmsWs carve(void *ws, int64_t N, size_t *total)
     w.nw = (int)ceil_div(n1, 64);
     Arena a(ws, (size_t)-1);
     w.n_cand = a.take<int32_t>(64);
+    w.band = a.take<u64>((size_t)w.nw * SW_BAND);
+    w.zero_bytes = a.off;
     w.rect = a.take<float4>((size_t)n1);
     w.srect = a.take<float4>((size_t)n1);
     w.keys = a.take<uint32_t>((size_t)n1);
@@ -241,7 +347,7 @@ extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_st
         set_error("nms workspace too small: %zu < %zu", workspace_bytes, total);
         return PP_ERR_WORKSPACE;
     }
-    PP_CUDA_TRY(cudaMemsetAsync(w.n_cand, 0, sizeof(int32_t), st));
+    PP_CUDA_TRY(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));     // candidate count + diagonal band
     prof_mark("memset");
     const unsigned nb = (unsigned)ceil_div(N, NMS_THREADS);
     nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.n_cand);
@@ -250,9 +356,18 @@ extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_st
     nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.n_cand, w.srect);
     if (int rc = check_launch("nms_gather_kernel")) return rc;
     dim3 grid((unsigned)ceil_div(N, MT_COLS), (unsigned)ceil_div(N, MT_ROWS));
-    nms_mask_kernel<<<grid, MT_ROWS, 0, st>>>(w.srect, w.n_cand, iou_thr, w.nw, w.mask);
+    if (iou_thr >= 0.f)      // a non-intersecting pair has iou == 0, which only exceeds a negative threshold
+        nms_mask_kernel<true><<<grid, MT_ROWS, 0, st>>>(w.srect, w.n_cand, iou_thr, w.nw, w.mask, w.band);
+    else
+        nms_mask_kernel<false><<<grid, MT_ROWS, 0, st>>>(w.srect, w.n_cand, iou_thr, w.nw, w.mask, w.band);
     if (int rc = check_launch("nms_mask_kernel")) return rc;
-    size_t smem = (size_t)w.nw * sizeof(u64);
-    nms_sweep_kernel<<<1, SWEEP_THREADS, smem, st>>>(w.mask, w.nw, w.n_cand, w.order, keep, keep_count);
+    size_t smem = ((size_t)SW_RING * SW_BAND + 3 * (size_t)w.nw) * sizeof(u64) + (size_t)w.nw * sizeof(int);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PP_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    PP_REQUIRE(smem <= 96 * 1024, "too many boxes for the sweep's shared memory");
+    nms_sweep_kernel<<<1, SWEEP_THREADS, smem, st>>>(w.mask, w.band, w.nw, w.n_cand, w.order, keep, keep_count, w.nw);
     return check_launch("nms_sweep_kernel");
 }
