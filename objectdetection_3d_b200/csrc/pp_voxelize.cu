@@ -1,221 +1,450 @@
 // Hard voxelization on sm_100a, bit-exact with the reference's sequential first-come pass
-// (ops/ops_numba.py:171-308), restated as order-independent parallel steps:
+// (ops/ops_numba.py:171-308), restated as order-independent parallel steps with NO global sort.
 //
-//   position p        = index of a point in processing order (given / reflectance-desc / perm)
-//   K1 cell           : cell id of every position; first[cell] = atomicMin(position)
-//   K2 assign         : a position is a "first arrival" iff first[cell] == p.  The pillar id is the
-//                       number of first arrivals before p (single-pass decoupled look-back scan);
-//                       the first arrival with id == max_voxels is the reference's `break`
-//                       (:223, :291): its position is the cutoff, everything at or after it is dropped.
-//   K3 rank           : every surviving position inserts itself into its pillar's sorted row of the
-//                       P smallest positions (lock-free atomicMin insertion chain; the final row is
-//                       independent of thread scheduling) -> slot = arrival rank of the reference.
-//   K4 gather         : voxels[m][s] = points[row[m][s]], zero padded; num_points[m] = filled slots.
+// Every point gets a unique ordering key K; the reference processes points in ascending K:
+//   given order / replayed permutation : K = position p                                  (32 bit)
+//   reflectance pre-order (:262)       : K = (~ordered(reflectance) << 32) | index        (64 bit)
+//                                        = descending reflectance, ties by lower index
+// The reference's outputs are functions of K only:
+//   pillar id   = rank of the cell's smallest key among all cells' smallest keys,
+//   `break`     = the (max_voxels+1)-th smallest cell minimum is the cutoff: keys >= cutoff are dropped,
+//   slot        = rank of the key inside its cell, capped at max_points.
 //
+// Kernels (T = 64 key chunks, monotone in K: position >> shift, or quantile splitters of a key sample):
+//   S  vox_splitter_kernel   reflectance only: sort a 1024-key sample in one CTA -> 63 coarse + 511 fine splitters
+//   A  vox_scatter_kernel    per point: cell -> compact cell row q (claimed on first touch, atomicCAS on a dense map),
+//                            first[q] = min K, cnt[q][chunk(K)] += 1
+//   Q1 vox_cell_prefix_kernel  per cell: cnt -> inclusive prefix over chunks; histogram of fine bins of first[q]
+//   Q2 vox_bucket_kernel       per cell: bucket the cells by fine bin
+//   Q3 vox_rank_kernel         per cell: pillar id = bin base + rank inside the bucket; coors, cutoff, voxel_num
+//   C  vox_place_kernel      per point: window [prefix(chunk-1), prefix(chunk)) of its cell's sorted row; points
+//                            of different chunks never touch the same slots, equal-chunk points (a handful) settle
+//                            their order with a lock-free atomicMin insertion chain -> slot order of the reference
+//   D  vox_gather_kernel     voxels[m][s] = points[row[m][s]], zero padded; num_points
 // Everything but the 16 B/point read and the output write is L2-resident workspace traffic.
+#include <math_constants.h>
+
 #include "pp_common.cuh"
-#include "pp_sort.cuh"
 
 namespace pp {
 namespace {
 
+typedef unsigned long long u64;
 constexpr int VOX_THREADS = 256;
-constexpr int SCAN_ITEMS = 4;
-constexpr int SCAN_TILE = VOX_THREADS * SCAN_ITEMS;
+constexpr int NCHUNK = 64;          // coarse key chunks per cell
+constexpr int NFINE = 512;          // fine bins used to rank the cells' first keys
+constexpr int SAMPLE = 1024;        // keys sampled for the quantile splitters (one per sorting thread)
 
-constexpr uint32_t FLAG_AGG = 1u << 30;
-constexpr uint32_t FLAG_PREFIX = 2u << 30;
-constexpr uint32_t FLAG_MASK = 3u << 30;
-constexpr uint32_t VAL_MASK = ~FLAG_MASK;
+template <typename K> struct KeyInf;
+template <> struct KeyInf<uint32_t> { static __device__ __host__ constexpr uint32_t value() { return 0xFFFFFFFFu; } };
+template <> struct KeyInf<u64> { static __device__ __host__ constexpr u64 value() { return ~0ull; } };
 
 struct VoxParams {
     double r[3], v[3];
-    float rf[3], vf[3];
+    float rf[3], vf[3], inv_vf[3], rv_abs[3];   // rv_abs = |r| / v: scale of the estimate's absolute error
     int g[3];
     int regime;   // 0: all f32   1: sub f32, div f64   2: all f64   (numba promotion)
     int P, max_voxels, C;
     int vec4;     // C == 4 and 16-byte aligned rows: float4 loads
+    int shift;    // 32-bit keys: chunk = K >> shift, fine bin = K >> fine_shift
+    int fine_shift;
 };
 
+struct VoxBuf {
+    int32_t *map;          // [cells]  cell -> q, -1 empty, -2 being claimed
+    int32_t *counters;     // [0] nq
+    int32_t r_init;        // rows [0, r_init) are initialised up front
+    int32_t *base;         // [NFINE + 1] exclusive scan of hist (written by the bucket kernel)
+    void *cutoff;          // key
+    int32_t *cell_of_q;    // [Q]
+    void *first;           // [Q] key
+    int32_t *cnt;          // [Q][NCHUNK] counts, then inclusive prefix
+    void *rows;            // [Q][P] keys, sorted ascending, INF padded
+    int32_t *pid_of_q;     // [Q]
+    int32_t *bin_of_q;     // [Q]
+    int32_t *q_of_point;   // [N]
+    uint32_t *key_of_point;  // [N] primary key (64-bit mode only)
+    int32_t *hist, *fill;  // [NFINE] each
+    int32_t *list;         // [Q] cells in bucket order
+    void *lkey;            // [Q] their first keys, same order
+    int32_t *q_of_pid;     // [rows]
+    u64 *coarse, *fine;    // splitters (64-bit mode): [NCHUNK-1], [NFINE-1]
+};
+
+// Cell index along one axis, bit-identical to the reference's floor((p - r) / v) in its promotion regime.
+// An fp32 reciprocal-multiply estimate decides every point that is not within a guard band of a cell
+// boundary (the band covers the rounding of r, 1/v and the two fp32 operations); only points inside the band
+// execute the reference's exact fp64 / IEEE-fp32 division.
 __device__ __forceinline__ bool axis_cell(const VoxParams &q, int j, float p, int &c)
 {
-    double cd;
-    if (q.regime == 2) {
-        cd = floor(((double)p - q.r[j]) / q.v[j]);
-    } else if (q.regime == 1) {
-        float d = __fsub_rn(p, q.rf[j]);
-        cd = floor((double)d / q.v[j]);
-    } else {
-        float d = __fsub_rn(p, q.rf[j]);
-        cd = (double)floorf(__fdiv_rn(d, q.vf[j]));
+    const float est = (p - q.rf[j]) * q.inv_vf[j];
+    const float fl = floorf(est);
+    const float fr = est - fl;
+    const float band = 1e-6f * (fabsf(est) + q.rv_abs[j]) + 1e-6f;
+    float cf = fl;
+    if (!(fr > band && fr < 1.0f - band)) {          // near a boundary (or NaN / huge): exact evaluation
+        double cd;
+        if (q.regime == 2) cd = floor(((double)p - q.r[j]) / q.v[j]);
+        else if (q.regime == 1) cd = floor((double)__fsub_rn(p, q.rf[j]) / q.v[j]);
+        else cd = (double)floorf(__fdiv_rn(__fsub_rn(p, q.rf[j]), q.vf[j]));
+        if (!(cd >= 0.0) || cd >= (double)q.g[j]) return false;   // also rejects NaN
+        c = (int)cd;
+        return true;
     }
-    if (!(cd >= 0.0) || cd >= (double)q.g[j]) return false;   // also rejects NaN
-    c = (int)cd;
+    if (!(cf >= 0.f) || cf >= (float)q.g[j]) return false;
+    c = (int)cf;
     return true;
 }
 
-// key for the reflectance pre-order: ascending key == descending reflectance
-__global__ void __launch_bounds__(VOX_THREADS) vox_refl_key_kernel(const float *__restrict__ points, int64_t n, int C,
-                                                                    uint32_t *__restrict__ keys)
+// number of splitters <= k (upper bound): a monotone map key -> [0, n]
+__device__ __forceinline__ int upper_bound_u64(const u64 *s, int n, u64 k)
 {
-    int64_t i = (int64_t)blockIdx.x * VOX_THREADS + threadIdx.x;
-    if (i < n) keys[i] = ~ordered_bits(points[i * C + 3]);
-}
-
-// K1: cell of every position + first arrival per cell.  Cell linearisation is (z*gy + y)*gx + x so
-// that the pillar map can be consumed directly by the (D,H,W) canvas scatter.
-__global__ void __launch_bounds__(VOX_THREADS)
-vox_cell_kernel(const float *__restrict__ points, int64_t n, const VoxParams q, const int32_t *__restrict__ perm,
-                int32_t *__restrict__ cell_of_pos, int32_t *__restrict__ first)
-{
-    int64_t p = (int64_t)blockIdx.x * VOX_THREADS + threadIdx.x;
-    if (p >= n) return;
-    int64_t idx = perm ? (int64_t)(uint32_t)perm[p] : p;
-    float x, y, z;
-    if (q.vec4) {
-        float4 v = __ldg(reinterpret_cast<const float4 *>(points) + idx);
-        x = v.x; y = v.y; z = v.z;
-    } else {
-        const float *pt = points + idx * q.C;
-        x = __ldg(pt); y = __ldg(pt + 1); z = __ldg(pt + 2);
-    }
-    int cx, cy, cz;
-    int32_t cell = -1;
-    if (axis_cell(q, 0, x, cx) && axis_cell(q, 1, y, cy) && axis_cell(q, 2, z, cz)) {
-        cell = (cz * q.g[1] + cy) * q.g[0] + cx;
-        atomicMin(first + cell, (int32_t)p);
-    }
-    cell_of_pos[p] = cell;
-}
-
-// K2: pillar ids by an ordered scan of the first-arrival flags (decoupled look-back, one launch).
-__global__ void __launch_bounds__(VOX_THREADS)
-vox_assign_kernel(const int32_t *__restrict__ cell_of_pos, int64_t n, const int32_t *__restrict__ first,
-                  const VoxParams q, int32_t *__restrict__ pid_of_cell, int32_t *__restrict__ coors,
-                  int32_t *__restrict__ cutoff, int32_t *__restrict__ voxel_num, uint32_t *status, uint32_t *ticket,
-                  int num_tiles)
-{
-    __shared__ uint32_t s_tile, s_excl;
-    __shared__ uint32_t warp_sum[VOX_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)tid * SCAN_ITEMS;
-
-    int32_t cell[SCAN_ITEMS];
-    uint32_t flags = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        int64_t p = base + k;
-        cell[k] = (p < n) ? cell_of_pos[p] : -1;
-        if (cell[k] >= 0 && first[cell[k]] == (int32_t)p) flags |= 1u << k;
-    }
-    uint32_t cnt = __popc(flags);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_sum[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = 0, block_total = 0;
-#pragma unroll
-    for (int w = 0; w < VOX_THREADS / 32; ++w) {
-        uint32_t s = warp_sum[w];
-        if (w < warp) wbase += s;
-        block_total += s;
-    }
-    if (tid == 0) {
-        uint32_t excl = 0;
-        if (tile == 0) {
-            atomicExch(status, FLAG_PREFIX | block_total);
-        } else {
-            atomicExch(status + tile, FLAG_AGG | block_total);
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                uint32_t s = *((volatile uint32_t *)(status + t));
-                if ((s & FLAG_MASK) == 0) continue;
-                excl += s & VAL_MASK;
-                if ((s & FLAG_MASK) == FLAG_PREFIX) break;
-                --t;
-            }
-            atomicExch(status + tile, FLAG_PREFIX | (excl + block_total));
-        }
-        s_excl = excl;
-        if ((int)tile == num_tiles - 1) {
-            uint32_t total = excl + block_total;
-            *voxel_num = (int32_t)(total < (uint32_t)q.max_voxels ? total : (uint32_t)q.max_voxels);
-        }
-    }
-    __syncthreads();
-    uint32_t vid = s_excl + wbase + incl - cnt;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        if (flags & (1u << k)) {
-            if (vid < (uint32_t)q.max_voxels) {
-                int c = cell[k];
-                pid_of_cell[c] = (int32_t)vid;
-                int cx = c % q.g[0];
-                int t = c / q.g[0];
-                coors[vid * 3 + 0] = cx;
-                coors[vid * 3 + 1] = t % q.g[1];
-                coors[vid * 3 + 2] = t / q.g[1];
-            } else if (vid == (uint32_t)q.max_voxels) {
-                *cutoff = (int32_t)(base + k);   // the reference breaks here
-            }
-            ++vid;
-        }
-    }
-}
-
-// K3: insert position p into the sorted row of the P smallest positions of its pillar.
-// Slots only ever decrease, so "row[j-1] < p was observed" stays true forever and the insertion
-// chain may start at j; every displaced value is pushed one slot down with atomicMin.  The final
-// row is the sorted set of the P smallest positions whatever the interleaving.
-__global__ void __launch_bounds__(VOX_THREADS)
-vox_rank_kernel(const int32_t *__restrict__ cell_of_pos, int64_t n, const int32_t *__restrict__ pid_of_cell,
-                const int32_t *__restrict__ cutoff, int P, int32_t *rows)
-{
-    int64_t p64 = (int64_t)blockIdx.x * VOX_THREADS + threadIdx.x;
-    if (p64 >= n) return;
-    const int32_t p = (int32_t)p64;
-    if (p >= *cutoff) return;
-    int32_t cell = cell_of_pos[p];
-    if (cell < 0) return;
-    int32_t *row = rows + (int64_t)pid_of_cell[cell] * P;
-    if (ld_cg(row + P - 1) < p) return;           // already P smaller positions: dropped (:303)
-    int lo = 0, hi = P - 1;
+    int lo = 0, hi = n;
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
-        if (ld_cg(row + mid) < p) lo = mid + 1; else hi = mid;
+        if (s[mid] <= k) lo = mid + 1; else hi = mid;
     }
-    int32_t carry = p;
-    for (int k = lo; k < P; ++k) {
-        int32_t old = atomicMin(row + k, carry);
-        if (old == PP_INF_POS) break;
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t key_min(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
+__device__ __forceinline__ u64 key_min(u64 *p, u64 v) { return atomicMin(p, v); }
+
+// ---- S: workspace initialisation, and (reflectance order) quantile splitters from a key sample ----------------
+// One launch replaces the memsets: CTA 0 sorts the key sample (bitonic, shared memory) while the other CTAs
+// fill map = -1, the first `r_init` cell rows (cnt = 0, first = rows = +inf) and the small counters.
+struct InitArgs {
+    int4 *ff_ptr[3];  int64_t ff_n[3];     // regions filled with 0xFF (16-byte units)
+    int4 *z_ptr[2];   int64_t z_n[2];      // regions filled with 0
+};
+
+__global__ void __launch_bounds__(1024)
+vox_init_kernel(const float *__restrict__ points, int64_t n, int C, int wide, u64 *__restrict__ coarse,
+                u64 *__restrict__ fine, const InitArgs ia)
+{
+    const int tid = threadIdx.x;
+    if (blockIdx.x > 0 || !wide) {
+        const int64_t nb = gridDim.x - (wide ? 1 : 0), b = blockIdx.x - (wide ? 1 : 0);
+        const int4 ff = make_int4(-1, -1, -1, -1), zz = make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            for (int64_t i = b * 1024 + tid; i < ia.ff_n[r]; i += nb * 1024) ia.ff_ptr[r][i] = ff;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            for (int64_t i = b * 1024 + tid; i < ia.z_n[r]; i += nb * 1024) ia.z_ptr[r][i] = zz;
+        return;
+    }
+    __shared__ u64 s[SAMPLE];
+    for (int i = tid; i < SAMPLE; i += 1024) {
+        // evenly spaced sample; short inputs are padded with +inf keys
+        int64_t idx = (n >= SAMPLE) ? (int64_t)i * (n / SAMPLE) : i;
+        u64 k = ~0ull;
+        if (idx < n) k = ((u64)(~ordered_bits(points[idx * C + 3])) << 32) | (uint32_t)idx;
+        s[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= SAMPLE; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < SAMPLE / 2; t += 1024) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = (lo & size) == 0;
+                u64 a = s[lo], b = s[hi];
+                if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < NCHUNK - 1; i += 1024) coarse[i] = s[(i + 1) * (SAMPLE / NCHUNK)];
+    for (int i = tid; i < NFINE - 1; i += 1024) fine[i] = s[(i + 1) * (SAMPLE / NFINE)];
+}
+
+// ---- A: per point ------------------------------------------------------------------------------------------
+template <typename K>
+__device__ __forceinline__ int claim_row(const VoxBuf &w, int32_t cell, int P)
+{
+    int q = __ldcg(w.map + cell);
+    while (q < 0) {
+        if (q == -1) {
+            int old = atomicCAS(w.map + cell, -1, -2);
+            if (old == -1) {
+                // first touch: allocate a compact row; rows >= r_init were not initialised by vox_init_kernel
+                q = atomicAdd(w.counters, 1);
+                w.cell_of_q[q] = cell;
+                if (q >= w.r_init) {
+                    ((K *)w.first)[q] = KeyInf<K>::value();
+                    int4 *c4 = reinterpret_cast<int4 *>(w.cnt + (size_t)q * NCHUNK);
+#pragma unroll
+                    for (int k = 0; k < NCHUNK / 4; ++k) c4[k] = make_int4(0, 0, 0, 0);
+                    K *row = (K *)w.rows + (size_t)q * P;
+                    for (int k = 0; k < P; ++k) row[k] = KeyInf<K>::value();
+                    __threadfence();
+                }
+                atomicExch(w.map + cell, q);
+                return q;
+            }
+            q = old;
+        } else {
+            q = *((volatile int32_t *)(w.map + cell));     // another thread is publishing the row
+        }
+    }
+    return q;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_scatter_kernel(const float *__restrict__ points, int64_t n, const VoxParams prm, const int32_t *__restrict__ perm,
+                   const VoxBuf w)
+{
+    __shared__ u64 s_coarse[NCHUNK];
+    constexpr bool WIDE = sizeof(K) == 8;
+    if (WIDE) {
+        if (threadIdx.x < NCHUNK - 1) s_coarse[threadIdx.x] = w.coarse[threadIdx.x];
+        __syncthreads();
+    }
+    const int64_t p = (int64_t)blockIdx.x * VOX_THREADS + threadIdx.x;
+    if (p >= n) return;
+    const int64_t idx = perm ? (int64_t)(uint32_t)perm[p] : p;
+    float x, y, z, refl = 0.f;
+    if (prm.vec4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(points) + idx);
+        x = v.x; y = v.y; z = v.z; refl = v.w;
+    } else {
+        const float *pt = points + idx * prm.C;
+        x = __ldg(pt); y = __ldg(pt + 1); z = __ldg(pt + 2);
+        if (WIDE) refl = __ldg(pt + 3);
+    }
+    int cx, cy, cz;
+    if (!(axis_cell(prm, 0, x, cx) && axis_cell(prm, 1, y, cy) && axis_cell(prm, 2, z, cz))) {
+        w.q_of_point[p] = -1;
+        return;
+    }
+    // cell linearisation (z*gy + y)*gx + x = the (D,H,W) order of the BEV canvas
+    const int32_t cell = (cz * prm.g[1] + cy) * prm.g[0] + cx;
+    const int q = claim_row<K>(w, cell, prm.P);
+    K key;
+    int ch;
+    if (WIDE) {
+        const uint32_t prim = ~ordered_bits(refl);
+        w.key_of_point[p] = prim;
+        key = (K)(((u64)prim << 32) | (uint32_t)p);
+        ch = upper_bound_u64(s_coarse, NCHUNK - 1, (u64)key);
+    } else {
+        key = (K)(uint32_t)p;
+        ch = min((int)((uint32_t)p >> prm.shift), NCHUNK - 1);
+    }
+    w.q_of_point[p] = q;
+    K *first = (K *)w.first + q;
+    if (key < *((volatile K *)first)) key_min(first, key);      // most points do not lower the minimum
+    atomicAdd(w.cnt + (size_t)q * NCHUNK + ch, 1);
+}
+
+// ---- Q1..Q3: per occupied cell --------------------------------------------------------------------------------
+constexpr int Q1_THREADS = 1024;   // 32 cells per CTA, one warp each
+
+// Q1: one warp per cell: counts -> inclusive prefix over the 64 chunks (two chunks per lane, coalesced), fine bin
+// of the cell's first key; the bins are aggregated in shared memory before they reach the global histogram.
+template <typename K>
+__global__ void __launch_bounds__(Q1_THREADS) vox_cell_prefix_kernel(const VoxParams prm, const VoxBuf w)
+{
+    __shared__ int s_hist[NFINE];
+    constexpr bool WIDE = sizeof(K) == 8;
+    const int nq = w.counters[0];
+    if ((int)(blockIdx.x * (Q1_THREADS / 32)) >= nq) return;
+    for (int i = threadIdx.x; i < NFINE; i += Q1_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int q = blockIdx.x * (Q1_THREADS / 32) + (threadIdx.x >> 5); q < nq; q += gridDim.x * (Q1_THREADS / 32)) {
+        int2 *c2 = reinterpret_cast<int2 *>(w.cnt + (size_t)q * NCHUNK) + lane;
+        int2 v = *c2;
+        v.y += v.x;
+        int incl = v.y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int excl = incl - v.y;
+        v.x += excl;
+        v.y += excl;
+        *c2 = v;
+        if (lane == 0) {
+            const K f = ((const K *)w.first)[q];
+            int bin;
+            if (WIDE) bin = upper_bound_u64(w.fine, NFINE - 1, (u64)f);
+            else bin = min((int)((uint32_t)f >> prm.fine_shift), NFINE - 1);
+            w.bin_of_q[q] = bin;
+            atomicAdd(s_hist + bin, 1);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NFINE; i += Q1_THREADS)
+        if (s_hist[i]) atomicAdd(w.hist + i, s_hist[i]);
+}
+
+// exclusive scan of the NFINE-bin histogram into shared memory
+__device__ __forceinline__ void scan_hist(const int32_t *__restrict__ hist, int *s_base /* [NFINE + 1] */)
+{
+    __shared__ int s_warp[VOX_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int PER = NFINE / VOX_THREADS;
+    int v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { v[k] = hist[tid * PER + k]; sum += v[k]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int base = incl - sum;
+    for (int k = 0; k < warp; ++k) base += s_warp[k];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { s_base[tid * PER + k] = base; base += v[k]; }
+    if (tid == VOX_THREADS - 1) s_base[NFINE] = base;
+    __syncthreads();
+}
+
+// Q2: one thread per cell: bucket the cells by fine bin (one global atomic per CTA and bin)
+template <typename K>
+__global__ void __launch_bounds__(VOX_THREADS) vox_bucket_kernel(const VoxBuf w)
+{
+    __shared__ int s_base[NFINE + 1];
+    __shared__ int s_cnt[NFINE], s_off[NFINE];
+    const int nq = w.counters[0];
+    if ((int)(blockIdx.x * VOX_THREADS) >= nq) return;
+    scan_hist(w.hist, s_base);
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i <= NFINE; i += VOX_THREADS) w.base[i] = s_base[i];   // for the rank kernel
+    for (int q0 = blockIdx.x * VOX_THREADS; q0 < nq; q0 += gridDim.x * VOX_THREADS) {   // CTA-uniform trip count
+        for (int i = threadIdx.x; i < NFINE; i += VOX_THREADS) s_cnt[i] = 0;
+        __syncthreads();
+        const int q = q0 + threadIdx.x;
+        int bin = 0, local = 0;
+        if (q < nq) {
+            bin = w.bin_of_q[q];
+            local = atomicAdd(s_cnt + bin, 1);               // position inside this CTA's share of the bucket
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < NFINE; i += VOX_THREADS)
+            if (s_cnt[i]) s_off[i] = atomicAdd(w.fill + i, s_cnt[i]);
+        __syncthreads();
+        if (q < nq) {
+            const int slot = s_base[bin] + s_off[bin] + local;
+            w.list[slot] = q;
+            ((K *)w.lkey)[slot] = ((const K *)w.first)[q];   // keys in bucket order: contiguous reads when ranking
+        }
+        __syncthreads();
+    }
+}
+
+// Q3: one warp per bucket slot: pillar id = bucket base + number of smaller first keys in the bucket (the lanes
+// stride over the bucket's contiguous keys), then coors / cutoff / voxel_num.
+template <typename K>
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_rank_kernel(const VoxParams prm, const VoxBuf w, int32_t *__restrict__ coors, int32_t *__restrict__ voxel_num,
+                int32_t *__restrict__ pillar_map)
+{
+    const int nq = w.counters[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *voxel_num = nq < prm.max_voxels ? nq : prm.max_voxels;
+    const int lane = threadIdx.x & 31;
+    const K *lkey = (const K *)w.lkey;
+    for (int t = blockIdx.x * (VOX_THREADS / 32) + (threadIdx.x >> 5); t < nq; t += gridDim.x * (VOX_THREADS / 32)) {
+    const int q = w.list[t];
+    const int bin = w.bin_of_q[q];
+    const K f = lkey[t];
+    const int b0 = w.base[bin], b1 = w.base[bin + 1];
+    int cnt = 0;
+    for (int j = b0 + lane; j < b1; j += 32) cnt += (lkey[j] < f) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if (lane != 0) continue;
+    const int rank = b0 + cnt;
+    const K f0 = f;
+    if (rank < prm.max_voxels) {
+        w.pid_of_q[q] = rank;
+        w.q_of_pid[rank] = q;
+        const int c = w.cell_of_q[q];
+        const int cx = c % prm.g[0], tt = c / prm.g[0];
+        coors[rank * 3 + 0] = cx;
+        coors[rank * 3 + 1] = tt % prm.g[1];
+        coors[rank * 3 + 2] = tt / prm.g[1];
+        if (pillar_map) pillar_map[c] = rank;
+    } else {
+        w.pid_of_q[q] = -1;
+        if (rank == prm.max_voxels) *(K *)w.cutoff = f0;    // the reference breaks here (:223, :291)
+    }
+    }
+}
+
+// ---- C: per point, slot inside the pillar ------------------------------------------------------------------------
+template <typename K>
+__global__ void __launch_bounds__(VOX_THREADS) vox_place_kernel(int64_t n, const VoxParams prm, const VoxBuf w)
+{
+    __shared__ u64 s_coarse[NCHUNK];
+    constexpr bool WIDE = sizeof(K) == 8;
+    if (WIDE) {
+        if (threadIdx.x < NCHUNK - 1) s_coarse[threadIdx.x] = w.coarse[threadIdx.x];
+        __syncthreads();
+    }
+    int64_t p = (int64_t)blockIdx.x * VOX_THREADS + threadIdx.x;
+    if (p >= n) return;
+    const int q = w.q_of_point[p];
+    if (q < 0) return;
+    K key;
+    int ch;
+    if (WIDE) {
+        key = (K)(((u64)w.key_of_point[p] << 32) | (uint32_t)p);
+        ch = upper_bound_u64(s_coarse, NCHUNK - 1, (u64)key);
+    } else {
+        key = (K)(uint32_t)p;
+        ch = min((int)((uint32_t)p >> prm.shift), NCHUNK - 1);
+    }
+    if (key >= *(const K *)w.cutoff) return;                 // at or after the break: dropped
+    const int32_t *incl = w.cnt + (size_t)q * NCHUNK;
+    const int base = ch ? incl[ch - 1] : 0;
+    const int P = prm.P;
+    if (base >= P) return;                                   // the pillar is full before this chunk (:303)
+    const int end = incl[ch];
+    const int wend = end < P ? end : P;
+    K *row = (K *)w.rows + (size_t)q * P;
+    if (end - base == 1) {                                   // alone in its window: the slot is known
+        row[base] = key;
+        return;
+    }
+    // a few points share the window [base, wend): sorted insertion with a lock-free atomicMin chain.  Slots only
+    // decrease, every displaced key is pushed one slot down, so the final window is sorted for any interleaving.
+    K carry = key;
+    for (int k = base; k < wend; ++k) {
+        const K old = key_min(row + k, carry);
+        if (old == KeyInf<K>::value()) break;
         carry = old > carry ? old : carry;
     }
 }
 
-// K4: gather the kept points into (M, P, C), zero padded, and count them.
-template <bool VEC4>
+// ---- D: gather ---------------------------------------------------------------------------------------------------
+template <typename K, bool VEC4>
 __global__ void __launch_bounds__(VOX_THREADS)
-vox_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ perm, const int32_t *__restrict__ rows,
+vox_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ perm, const VoxBuf w,
                   const int32_t *__restrict__ voxel_num, int64_t max_rows, int P, int C, float *__restrict__ voxels,
                   int32_t *__restrict__ num_points)
 {
     int64_t t = (int64_t)blockIdx.x * VOX_THREADS + threadIdx.x;   // one thread per (pillar, slot)
     if (t >= max_rows * P) return;
-    int64_t m = t / P;
-    int s = (int)(t - m * P);
+    const int64_t m = t / P;
+    const int s = (int)(t - m * P);
     if (m >= *voxel_num) return;
-    int32_t pos = rows[t];
-    bool valid = pos != PP_INF_POS;
-    if (valid && (s == P - 1 || rows[t + 1] == PP_INF_POS)) num_points[m] = s + 1;
+    const K *row = (const K *)w.rows + (size_t)w.q_of_pid[m] * P;
+    const K key = row[s];
+    const bool valid = key != KeyInf<K>::value();
+    if (valid && (s == P - 1 || row[s + 1] == KeyInf<K>::value())) num_points[m] = s + 1;
     int64_t idx = 0;
-    if (valid) idx = perm ? (int64_t)(uint32_t)perm[pos] : (int64_t)pos;
+    if (valid) {
+        const uint32_t pos = (uint32_t)key;                  // low word = position / original index
+        idx = perm ? (int64_t)(uint32_t)perm[pos] : (int64_t)pos;
+    }
     if (VEC4) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) v = __ldg(reinterpret_cast<const float4 *>(points) + idx);
@@ -225,22 +454,7 @@ vox_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ 
     }
 }
 
-struct VoxWs {
-    // 0x7F-filled
-    int32_t *first, *rows, *cutoff;
-    size_t fill7f_bytes;
-    // zero-filled
-    uint32_t *status, *ticket;
-    size_t zero_off, zero_bytes;
-    // uninitialised
-    int32_t *cell_of_pos, *pid_of_cell;
-    uint32_t *keys, *keys_sorted, *perm;
-    void *sort_ws;
-    size_t sort_ws_bytes;
-    int num_tiles;
-    int64_t max_rows, cells;
-};
-
+// ---- host side -----------------------------------------------------------------------------------------------------
 int64_t max_rows_of(int64_t n, const pp_voxel_cfg *c)
 {
     int64_t cells = (int64_t)c->grid[0] * c->grid[1] * c->grid[2];
@@ -250,36 +464,92 @@ int64_t max_rows_of(int64_t n, const pp_voxel_cfg *c)
     return r > 0 ? r : 1;
 }
 
-VoxWs carve(void *ws, int64_t n, const pp_voxel_cfg *c, int order, bool need_pid, size_t *total)
+struct Carve {
+    VoxBuf b;
+    InitArgs ia;
+    int64_t Q;
+};
+
+inline int64_t units16(size_t bytes) { return (int64_t)(align_up(bytes, 16) / 16); }
+
+Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total)
 {
-    VoxWs w;
-    int64_t n1 = n > 0 ? n : 1;
-    w.cells = (int64_t)c->grid[0] * c->grid[1] * c->grid[2];
-    w.max_rows = max_rows_of(n, c);
-    w.num_tiles = (int)ceil_div(n1, SCAN_TILE);
+    Carve r;
+    const int64_t n1 = n > 0 ? n : 1;
+    const int64_t cells = (int64_t)c->grid[0] * c->grid[1] * c->grid[2];
+    r.Q = n1 < cells ? n1 : cells;
+    const size_t ksz = wide ? 8 : 4;
+    // rows initialised up front: a bit more than the pillar cap; beyond that the claiming thread initialises
+    int64_t r_init = (int64_t)c->max_voxels + c->max_voxels / 4 + 1024;
+    if (r_init > r.Q) r_init = r.Q;
+    r.b.r_init = (int32_t)r_init;
     Arena a(ws, (size_t)-1);
-    w.first = a.take<int32_t>((size_t)w.cells);
-    w.rows = a.take<int32_t>((size_t)w.max_rows * c->max_points);
-    w.cutoff = a.take<int32_t>(64);
-    w.fill7f_bytes = a.off;
-    w.zero_off = align_up(a.off);
-    w.status = a.take<uint32_t>((size_t)w.num_tiles);
-    w.ticket = a.take<uint32_t>(64);
-    w.zero_bytes = a.off - w.zero_off;
-    w.cell_of_pos = a.take<int32_t>((size_t)n1);
-    w.pid_of_cell = need_pid ? a.take<int32_t>((size_t)w.cells) : nullptr;
-    w.keys = w.keys_sorted = w.perm = nullptr;
-    w.sort_ws = nullptr;
-    w.sort_ws_bytes = 0;
-    if (order == PP_ORDER_REFLECTANCE_DESC) {
-        w.keys = a.take<uint32_t>((size_t)n1);
-        w.keys_sorted = a.take<uint32_t>((size_t)n1);
-        w.perm = a.take<uint32_t>((size_t)n1);
-        w.sort_ws_bytes = sort_workspace_bytes(n1);
-        w.sort_ws = a.take<char>(w.sort_ws_bytes);
-    }
+    r.b.map = a.take<int32_t>((size_t)cells);
+    r.b.cutoff = a.take<u64>(8);
+    const size_t ff0_bytes = a.off;                          // map + cutoff, contiguous, 0xFF
+    r.b.counters = a.take<int32_t>(64);
+    r.b.hist = a.take<int32_t>(NFINE);
+    r.b.fill = a.take<int32_t>(NFINE);
+    const size_t z0_off = (size_t)((char *)r.b.counters - (char *)ws), z0_bytes = a.off - z0_off;
+    r.b.base = a.take<int32_t>(NFINE + 1);
+    r.b.cell_of_q = a.take<int32_t>((size_t)r.Q);
+    r.b.first = a.take<char>((size_t)r.Q * ksz);
+    r.b.cnt = a.take<int32_t>((size_t)r.Q * NCHUNK);
+    r.b.rows = a.take<char>((size_t)r.Q * c->max_points * ksz);
+    r.b.pid_of_q = a.take<int32_t>((size_t)r.Q);
+    r.b.bin_of_q = a.take<int32_t>((size_t)r.Q);
+    r.b.q_of_point = a.take<int32_t>((size_t)n1);
+    r.b.key_of_point = wide ? a.take<uint32_t>((size_t)n1) : nullptr;
+    r.b.list = a.take<int32_t>((size_t)r.Q);
+    r.b.lkey = a.take<char>((size_t)r.Q * ksz);
+    r.b.q_of_pid = a.take<int32_t>((size_t)max_rows_of(n, c));
+    r.b.coarse = a.take<u64>(NCHUNK);
+    r.b.fine = a.take<u64>(NFINE);
     *total = align_up(a.off);
-    return w;
+    // every array starts 256-byte aligned, so rounding the fills up to 16 bytes stays inside the padding
+    r.ia.ff_ptr[0] = (int4 *)r.b.map;    r.ia.ff_n[0] = units16(ff0_bytes);
+    r.ia.ff_ptr[1] = (int4 *)r.b.first;  r.ia.ff_n[1] = units16((size_t)r_init * ksz);
+    r.ia.ff_ptr[2] = (int4 *)r.b.rows;   r.ia.ff_n[2] = units16((size_t)r_init * c->max_points * ksz);
+    r.ia.z_ptr[0] = (int4 *)((char *)ws + z0_off);  r.ia.z_n[0] = units16(z0_bytes);
+    r.ia.z_ptr[1] = (int4 *)r.b.cnt;     r.ia.z_n[1] = units16((size_t)r_init * NCHUNK * 4);
+    return r;
+}
+
+template <typename K>
+int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *perm, const Carve &cv, float *voxels,
+        int32_t *coors, int32_t *num_points, int32_t *voxel_num, int32_t *pillar_map, int64_t max_rows, cudaStream_t st)
+{
+    const VoxBuf &w = cv.b;
+    constexpr bool WIDE = sizeof(K) == 8;
+    const unsigned nb = (unsigned)ceil_div(n, VOX_THREADS);
+    const unsigned qb = (unsigned)ceil_div(cv.Q, VOX_THREADS);
+    int64_t fill_units = 0;
+    for (int r = 0; r < 3; ++r) fill_units += cv.ia.ff_n[r];
+    for (int r = 0; r < 2; ++r) fill_units += cv.ia.z_n[r];
+    int init_blocks = (int)ceil_div(fill_units, 1024 * 4);
+    init_blocks = init_blocks < 1 ? 1 : (init_blocks > 148 * 2 ? 148 * 2 : init_blocks);
+    vox_init_kernel<<<init_blocks + (WIDE ? 1 : 0), 1024, 0, st>>>(points, n, prm.C, WIDE ? 1 : 0, w.coarse, w.fine, cv.ia);
+    if (int rc = check_launch("vox_init_kernel")) return rc;
+    vox_scatter_kernel<K><<<nb, VOX_THREADS, 0, st>>>(points, n, prm, perm, w);
+    if (int rc = check_launch("vox_scatter_kernel")) return rc;
+    const unsigned cap = 148 * 8;    // persistent-style grids: the cell count is only known on the device
+    auto capped = [&](int64_t blocks) { return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap); };
+    vox_cell_prefix_kernel<K><<<capped(ceil_div(cv.Q, Q1_THREADS / 32)) / 4 + 1, Q1_THREADS, 0, st>>>(prm, w);
+    if (int rc = check_launch("vox_cell_prefix_kernel")) return rc;
+    vox_bucket_kernel<K><<<capped(qb), VOX_THREADS, 0, st>>>(w);
+    if (int rc = check_launch("vox_bucket_kernel")) return rc;
+    vox_rank_kernel<K><<<capped(ceil_div(cv.Q, VOX_THREADS / 32)), VOX_THREADS, 0, st>>>(prm, w, coors, voxel_num, pillar_map);
+    if (int rc = check_launch("vox_rank_kernel")) return rc;
+    vox_place_kernel<K><<<nb, VOX_THREADS, 0, st>>>(n, prm, w);
+    if (int rc = check_launch("vox_place_kernel")) return rc;
+    const int64_t slots = max_rows * prm.P;
+    const unsigned gb = (unsigned)ceil_div(slots, VOX_THREADS);
+    const bool vec4 = prm.vec4 && ((uintptr_t)voxels % 16 == 0);
+    if (vec4)
+        vox_gather_kernel<K, true><<<gb, VOX_THREADS, 0, st>>>(points, perm, w, voxel_num, max_rows, prm.P, prm.C, voxels, num_points);
+    else
+        vox_gather_kernel<K, false><<<gb, VOX_THREADS, 0, st>>>(points, perm, w, voxel_num, max_rows, prm.P, prm.C, voxels, num_points);
+    return check_launch("vox_gather_kernel");
 }
 
 }  // namespace
@@ -297,7 +567,7 @@ extern "C" size_t pp_voxelize_workspace_bytes(int64_t n_points, const pp_voxel_c
 {
     if (!cfg) return 0;
     size_t total;
-    carve(nullptr, n_points, cfg, order, true, &total);
+    carve(nullptr, n_points, cfg, order == PP_ORDER_REFLECTANCE_DESC, &total);
     return total;
 }
 
@@ -315,22 +585,25 @@ extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *c
     PP_REQUIRE(order != PP_ORDER_PERM || perm, "PP_ORDER_PERM needs perm");
     PP_REQUIRE(cfg->max_points > 0 && cfg->max_voxels >= 0, "bad caps");
     PP_REQUIRE(cfg->grid[0] > 0 && cfg->grid[1] > 0 && cfg->grid[2] > 0, "empty grid");
-    int64_t cells = (int64_t)cfg->grid[0] * cfg->grid[1] * cfg->grid[2];
+    const int64_t cells = (int64_t)cfg->grid[0] * cfg->grid[1] * cfg->grid[2];
     PP_REQUIRE(cells < (1ll << 31), "grid too large (>= 2^31 cells)");
+    if (pillar_map) {
+        PP_CUDA_TRY(cudaMemsetAsync(pillar_map, 0xFF, (size_t)cells * 4, st));
+        prof_mark("memset");
+    }
     if (n == 0 || cfg->max_voxels == 0) {
         PP_CUDA_TRY(cudaMemsetAsync(voxel_num, 0, sizeof(int32_t), st));
-        if (pillar_map) PP_CUDA_TRY(cudaMemsetAsync(pillar_map, 0xFF, (size_t)cells * 4, st));
         return PP_OK;
     }
     PP_REQUIRE(points && voxels && coors && num_points && workspace, "null pointer");
 
+    const bool wide = order == PP_ORDER_REFLECTANCE_DESC;
     size_t total;
-    VoxWs w = carve(workspace, n, cfg, order, pillar_map == nullptr, &total);
+    Carve cv = carve(workspace, n, cfg, wide, &total);
     if (workspace_bytes < total) {
         set_error("voxelize workspace too small: %zu < %zu", workspace_bytes, total);
         return PP_ERR_WORKSPACE;
     }
-    int32_t *pid_of_cell = pillar_map ? pillar_map : w.pid_of_cell;
 
     VoxParams q;
     for (int j = 0; j < 3; ++j) {
@@ -338,6 +611,8 @@ extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *c
         q.v[j] = cfg->vsize[j];
         q.rf[j] = (float)cfg->range[j];
         q.vf[j] = (float)cfg->vsize[j];
+        q.inv_vf[j] = 1.0f / q.vf[j];
+        q.rv_abs[j] = (float)(fabs(q.r[j]) / q.v[j]);
         q.g[j] = cfg->grid[j];
     }
     q.regime = cfg->range_is_f64 ? 2 : (cfg->vsize_is_f64 ? 1 : 0);
@@ -345,37 +620,14 @@ extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *c
     q.max_voxels = cfg->max_voxels;
     q.C = cfg->num_feats;
     q.vec4 = (q.C == 4 && ((uintptr_t)points % 16 == 0)) ? 1 : 0;
+    int bits = 0;
+    while (((int64_t)1 << bits) < n) ++bits;                 // positions < 2^bits
+    q.shift = bits > 6 ? bits - 6 : 0;                       // 64 chunks
+    q.fine_shift = bits > 9 ? bits - 9 : 0;                  // 512 fine bins
 
-    PP_CUDA_TRY(cudaMemsetAsync(workspace, 0x7F, w.fill7f_bytes, st));
-    PP_CUDA_TRY(cudaMemsetAsync((char *)workspace + w.zero_off, 0, w.zero_bytes, st));
-    if (pillar_map) PP_CUDA_TRY(cudaMemsetAsync(pillar_map, 0xFF, (size_t)cells * 4, st));
-    prof_mark("memset");
-
-    const int32_t *order_perm = nullptr;
-    if (order == PP_ORDER_PERM) {
-        order_perm = perm;
-    } else if (order == PP_ORDER_REFLECTANCE_DESC) {
-        vox_refl_key_kernel<<<(unsigned)ceil_div(n, VOX_THREADS), VOX_THREADS, 0, st>>>(points, n, q.C, w.keys);
-        if (int rc = check_launch("vox_refl_key_kernel")) return rc;
-        if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.perm, n, w.sort_ws, w.sort_ws_bytes, st)) return rc;
-        order_perm = (const int32_t *)w.perm;
-    }
-
-    const unsigned nb = (unsigned)ceil_div(n, VOX_THREADS);
-    vox_cell_kernel<<<nb, VOX_THREADS, 0, st>>>(points, n, q, order_perm, w.cell_of_pos, w.first);
-    if (int rc = check_launch("vox_cell_kernel")) return rc;
-    vox_assign_kernel<<<w.num_tiles, VOX_THREADS, 0, st>>>(w.cell_of_pos, n, w.first, q, pid_of_cell, coors, w.cutoff,
-                                                          voxel_num, w.status, w.ticket, w.num_tiles);
-    if (int rc = check_launch("vox_assign_kernel")) return rc;
-    vox_rank_kernel<<<nb, VOX_THREADS, 0, st>>>(w.cell_of_pos, n, pid_of_cell, w.cutoff, q.P, w.rows);
-    if (int rc = check_launch("vox_rank_kernel")) return rc;
-    const int64_t slots = w.max_rows * q.P;
-    const bool vec4 = q.vec4 && ((uintptr_t)voxels % 16 == 0);
-    if (vec4)
-        vox_gather_kernel<true><<<(unsigned)ceil_div(slots, VOX_THREADS), VOX_THREADS, 0, st>>>(
-            points, order_perm, w.rows, voxel_num, w.max_rows, q.P, q.C, voxels, num_points);
-    else
-        vox_gather_kernel<false><<<(unsigned)ceil_div(slots, VOX_THREADS), VOX_THREADS, 0, st>>>(
-            points, order_perm, w.rows, voxel_num, w.max_rows, q.P, q.C, voxels, num_points);
-    return check_launch("vox_gather_kernel");
+    const int32_t *order_perm = order == PP_ORDER_PERM ? perm : nullptr;
+    const int64_t max_rows = max_rows_of(n, cfg);
+    if (wide)
+        return run<u64>(points, n, q, order_perm, cv, voxels, coors, num_points, voxel_num, pillar_map, max_rows, st);
+    return run<uint32_t>(points, n, q, order_perm, cv, voxels, coors, num_points, voxel_num, pillar_map, max_rows, st);
 }
