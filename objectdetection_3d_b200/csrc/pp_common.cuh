@@ -72,6 +72,33 @@ __device__ __forceinline__ uint32_t ordered_bits(float f)
 // L2-coherent loads (bypass the non-coherent L1) for data other CTAs are updating
 __device__ __forceinline__ int ld_cg(const int *p) { return __ldcg(p); }
 
+// Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while its predecessor on
+// the stream is still draining; it must execute pdl_enter() before it touches anything the predecessor wrote.
+// pdl_enter() also lets the NEXT kernel start being scheduled (safe: a dependent grid is only launched once
+// every CTA of this grid has started).  This hides most of the ~3 us launch gap between the small kernels.
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ unsigned lanemask_lt()
 {
     unsigned m;

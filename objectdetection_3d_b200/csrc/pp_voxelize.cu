@@ -32,7 +32,7 @@ namespace {
 typedef unsigned long long u64;
 constexpr int VOX_THREADS = 256;
 constexpr int NCHUNK = 64;          // coarse key chunks per cell
-constexpr int NFINE = 512;          // fine bins used to rank the cells' first keys
+constexpr int NFINE = 1024;         // fine bins used to rank the cells' first keys
 constexpr int SAMPLE = 1024;        // keys sampled for the quantile splitters (one per sorting thread)
 
 template <typename K> struct KeyInf;
@@ -46,8 +46,7 @@ struct VoxParams {
     int regime;   // 0: all f32   1: sub f32, div f64   2: all f64   (numba promotion)
     int P, max_voxels, C;
     int vec4;     // C == 4 and 16-byte aligned rows: float4 loads
-    int shift;    // 32-bit keys: chunk = K >> shift, fine bin = K >> fine_shift
-    int fine_shift;
+    int bits;     // 32-bit keys: positions < 2^bits; chunks / fine bins are geometric in the position (geo_bin)
 };
 
 struct VoxBuf {
@@ -62,6 +61,7 @@ struct VoxBuf {
     void *rows;            // [Q][P] keys, sorted ascending, INF padded
     int32_t *pid_of_q;     // [Q]
     int32_t *bin_of_q;     // [Q]
+    uint8_t *sat_of_q;     // [Q] first chunk whose inclusive prefix reaches max_points (NCHUNK if none)
     int32_t *q_of_point;   // [N]
     uint32_t *key_of_point;  // [N] primary key (64-bit mode only)
     int32_t *hist, *fill;  // [NFINE] each
@@ -107,6 +107,35 @@ __device__ __forceinline__ int upper_bound_u64(const u64 *s, int n, u64 k)
     return lo;
 }
 
+// Geometric binning of a position u < 2^bits into NOCT octaves x 2^SUB sub-bins (monotone in u).  Octave 0 is
+// [0, 2^(bits-NOCT+1)), octave k >= 1 is [2^(bits-NOCT+k), 2^(bits-NOCT+k+1)); each octave is split evenly.
+// A cell with n points keeps its max_points smallest keys, i.e. the key quantiles below max_points / n: the
+// resolution is spent where the dense cells need it, so windows stay a few points wide whatever n is.
+template <int NOCT, int SUB>
+__device__ __forceinline__ int geo_bin(uint32_t u, int bits)
+{
+    const int l0 = bits - (NOCT - 1);                     // log2 of octave 0's width
+    if (l0 < SUB) return (int)min(u >> max(bits - (31 - __clz(NOCT << SUB)), 0), (uint32_t)((NOCT << SUB) - 1));   // tiny inputs: uniform
+    const uint32_t top = u >> l0;
+    if (top == 0) return (int)(u >> (l0 - SUB));
+    const int k = 31 - __clz(top);                        // octave k + 1
+    return ((k + 1) << SUB) | (int)((u - (1u << (l0 + k))) >> (l0 + k - SUB));
+}
+
+// The same geometric layout expressed as quantiles of a sorted sample: index of the lower edge of bin b
+template <int NOCT, int SUB>
+__device__ __forceinline__ int geo_sample_index(int b, int sample)
+{
+    const int oct = b >> SUB, sub = b & ((1 << SUB) - 1);
+    // octave 0 covers sample / 2^(NOCT-1) elements, octave k >= 1 covers sample / 2^(NOCT-k)
+    const int w = oct == 0 ? sample >> (NOCT - 1) : sample >> (NOCT - oct);
+    const int lo = oct == 0 ? 0 : sample >> (NOCT - oct);
+    return lo + ((w * sub) >> SUB);
+}
+
+constexpr int C_OCT = 8, C_SUB = 3;      // 64 coarse chunks
+constexpr int F_OCT = 16, F_SUB = 6;     // 1024 fine bins (32-bit keys); 64-bit keys use uniform sample quantiles
+
 __device__ __forceinline__ uint32_t key_min(uint32_t *p, uint32_t v) { return atomicMin(p, v); }
 __device__ __forceinline__ u64 key_min(u64 *p, u64 v) { return atomicMin(p, v); }
 
@@ -122,6 +151,7 @@ __global__ void __launch_bounds__(1024)
 vox_init_kernel(const float *__restrict__ points, int64_t n, int C, int wide, u64 *__restrict__ coarse,
                 u64 *__restrict__ fine, const InitArgs ia)
 {
+    pdl_enter();
     const int tid = threadIdx.x;
     if (blockIdx.x > 0 || !wide) {
         const int64_t nb = gridDim.x - (wide ? 1 : 0), b = blockIdx.x - (wide ? 1 : 0);
@@ -155,7 +185,8 @@ vox_init_kernel(const float *__restrict__ points, int64_t n, int C, int wide, u6
             __syncthreads();
         }
     }
-    for (int i = tid; i < NCHUNK - 1; i += 1024) coarse[i] = s[(i + 1) * (SAMPLE / NCHUNK)];
+    // coarse chunk b starts at the geometric quantile geo_sample_index(b); splitter i is the start of chunk i + 1
+    for (int i = tid; i < NCHUNK - 1; i += 1024) coarse[i] = s[geo_sample_index<C_OCT, C_SUB>(i + 1, SAMPLE)];
     for (int i = tid; i < NFINE - 1; i += 1024) fine[i] = s[(i + 1) * (SAMPLE / NFINE)];
 }
 
@@ -196,6 +227,7 @@ __global__ void __launch_bounds__(VOX_THREADS)
 vox_scatter_kernel(const float *__restrict__ points, int64_t n, const VoxParams prm, const int32_t *__restrict__ perm,
                    const VoxBuf w)
 {
+    pdl_enter();
     __shared__ u64 s_coarse[NCHUNK];
     constexpr bool WIDE = sizeof(K) == 8;
     if (WIDE) {
@@ -231,11 +263,11 @@ vox_scatter_kernel(const float *__restrict__ points, int64_t n, const VoxParams 
         ch = upper_bound_u64(s_coarse, NCHUNK - 1, (u64)key);
     } else {
         key = (K)(uint32_t)p;
-        ch = min((int)((uint32_t)p >> prm.shift), NCHUNK - 1);
+        ch = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
     }
     w.q_of_point[p] = q;
     K *first = (K *)w.first + q;
-    if (key < *((volatile K *)first)) key_min(first, key);      // most points do not lower the minimum
+    if (key < __ldcg(first)) key_min(first, key);                // most points do not lower the minimum (L2 read, not .sys)
     atomicAdd(w.cnt + (size_t)q * NCHUNK + ch, 1);
 }
 
@@ -247,6 +279,7 @@ constexpr int Q1_THREADS = 1024;   // 32 cells per CTA, one warp each
 template <typename K>
 __global__ void __launch_bounds__(Q1_THREADS) vox_cell_prefix_kernel(const VoxParams prm, const VoxBuf w)
 {
+    pdl_enter();
     __shared__ int s_hist[NFINE];
     constexpr bool WIDE = sizeof(K) == 8;
     const int nq = w.counters[0];
@@ -268,11 +301,16 @@ __global__ void __launch_bounds__(Q1_THREADS) vox_cell_prefix_kernel(const VoxPa
         v.x += excl;
         v.y += excl;
         *c2 = v;
+        // first chunk at which the cell already holds max_points points: later chunks are dropped unseen
+        int sat = v.x >= prm.P ? 2 * lane : (v.y >= prm.P ? 2 * lane + 1 : NCHUNK);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sat = min(sat, __shfl_xor_sync(0xFFFFFFFFu, sat, o));
         if (lane == 0) {
+            w.sat_of_q[q] = (uint8_t)sat;
             const K f = ((const K *)w.first)[q];
             int bin;
             if (WIDE) bin = upper_bound_u64(w.fine, NFINE - 1, (u64)f);
-            else bin = min((int)((uint32_t)f >> prm.fine_shift), NFINE - 1);
+            else bin = geo_bin<F_OCT, F_SUB>((uint32_t)f, prm.bits);
             w.bin_of_q[q] = bin;
             atomicAdd(s_hist + bin, 1);
         }
@@ -311,6 +349,7 @@ __device__ __forceinline__ void scan_hist(const int32_t *__restrict__ hist, int 
 template <typename K>
 __global__ void __launch_bounds__(VOX_THREADS) vox_bucket_kernel(const VoxBuf w)
 {
+    pdl_enter();
     __shared__ int s_base[NFINE + 1];
     __shared__ int s_cnt[NFINE], s_off[NFINE];
     const int nq = w.counters[0];
@@ -347,6 +386,7 @@ __global__ void __launch_bounds__(VOX_THREADS)
 vox_rank_kernel(const VoxParams prm, const VoxBuf w, int32_t *__restrict__ coors, int32_t *__restrict__ voxel_num,
                 int32_t *__restrict__ pillar_map)
 {
+    pdl_enter();
     const int nq = w.counters[0];
     if (blockIdx.x == 0 && threadIdx.x == 0) *voxel_num = nq < prm.max_voxels ? nq : prm.max_voxels;
     const int lane = threadIdx.x & 31;
@@ -380,47 +420,59 @@ vox_rank_kernel(const VoxParams prm, const VoxBuf w, int32_t *__restrict__ coors
 }
 
 // ---- C: per point, slot inside the pillar ------------------------------------------------------------------------
+constexpr int PLACE_THREADS = 512;
+constexpr int PLACE_TABLE = 40 * 1024;      // cells whose saturation chunk is cached in shared memory
+
+// Persistent CTAs: the per-cell saturation chunk (1 byte per cell) is staged in shared memory once per CTA, so the
+// majority of the points -- those of already full pillars -- are rejected without any random global access.
 template <typename K>
-__global__ void __launch_bounds__(VOX_THREADS) vox_place_kernel(int64_t n, const VoxParams prm, const VoxBuf w)
+__global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, const VoxParams prm, const VoxBuf w)
 {
+    pdl_enter();
     __shared__ u64 s_coarse[NCHUNK];
+    __shared__ __align__(16) uint8_t s_sat[PLACE_TABLE];
     constexpr bool WIDE = sizeof(K) == 8;
-    if (WIDE) {
-        if (threadIdx.x < NCHUNK - 1) s_coarse[threadIdx.x] = w.coarse[threadIdx.x];
-        __syncthreads();
-    }
-    int64_t p = (int64_t)blockIdx.x * VOX_THREADS + threadIdx.x;
-    if (p >= n) return;
-    const int q = w.q_of_point[p];
-    if (q < 0) return;
-    K key;
-    int ch;
-    if (WIDE) {
-        key = (K)(((u64)w.key_of_point[p] << 32) | (uint32_t)p);
-        ch = upper_bound_u64(s_coarse, NCHUNK - 1, (u64)key);
-    } else {
-        key = (K)(uint32_t)p;
-        ch = min((int)((uint32_t)p >> prm.shift), NCHUNK - 1);
-    }
-    if (key >= *(const K *)w.cutoff) return;                 // at or after the break: dropped
-    const int32_t *incl = w.cnt + (size_t)q * NCHUNK;
-    const int base = ch ? incl[ch - 1] : 0;
+    if (WIDE && threadIdx.x < NCHUNK - 1) s_coarse[threadIdx.x] = w.coarse[threadIdx.x];
+    const int nq = w.counters[0];
+    const int ntab = nq < PLACE_TABLE ? nq : PLACE_TABLE;
+    for (int i = threadIdx.x; i * 16 < ntab; i += PLACE_THREADS)
+        reinterpret_cast<uint4 *>(s_sat)[i] = reinterpret_cast<const uint4 *>(w.sat_of_q)[i];
+    __syncthreads();
+    const K cutoff = *(const K *)w.cutoff;
     const int P = prm.P;
-    if (base >= P) return;                                   // the pillar is full before this chunk (:303)
-    const int end = incl[ch];
-    const int wend = end < P ? end : P;
-    K *row = (K *)w.rows + (size_t)q * P;
-    if (end - base == 1) {                                   // alone in its window: the slot is known
-        row[base] = key;
-        return;
-    }
-    // a few points share the window [base, wend): sorted insertion with a lock-free atomicMin chain.  Slots only
-    // decrease, every displaced key is pushed one slot down, so the final window is sorted for any interleaving.
-    K carry = key;
-    for (int k = base; k < wend; ++k) {
-        const K old = key_min(row + k, carry);
-        if (old == KeyInf<K>::value()) break;
-        carry = old > carry ? old : carry;
+    for (int64_t p = (int64_t)blockIdx.x * PLACE_THREADS + threadIdx.x; p < n; p += (int64_t)gridDim.x * PLACE_THREADS) {
+        const int q = w.q_of_point[p];
+        if (q < 0) continue;
+        K key;
+        int ch;
+        if (WIDE) {
+            key = (K)(((u64)w.key_of_point[p] << 32) | (uint32_t)p);
+            ch = upper_bound_u64(s_coarse, NCHUNK - 1, (u64)key);
+        } else {
+            key = (K)(uint32_t)p;
+            ch = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
+        }
+        const int sat = q < PLACE_TABLE ? (int)s_sat[q] : (int)w.sat_of_q[q];
+        if (ch > sat) continue;                              // the pillar is full before this chunk (:303)
+        if (key >= cutoff) continue;                         // at or after the break: dropped
+        const int32_t *incl = w.cnt + (size_t)q * NCHUNK;
+        const int base = ch ? incl[ch - 1] : 0;
+        const int end = incl[ch];
+        const int wend = end < P ? end : P;
+        K *row = (K *)w.rows + (size_t)q * P;
+        if (end - base == 1) {                               // alone in its window: the slot is known
+            row[base] = key;
+            continue;
+        }
+        // a few points share the window [base, wend): sorted insertion with a lock-free atomicMin chain.  Slots only
+        // decrease, every displaced key is pushed one slot down, so the final window is sorted for any interleaving.
+        if (__ldcg(row + wend - 1) < key) continue;              // the (truncated) window already holds smaller keys
+        K carry = key;
+        for (int k = base; k < wend; ++k) {
+            const K old = key_min(row + k, carry);
+            if (old == KeyInf<K>::value()) break;
+            carry = old > carry ? old : carry;
+        }
     }
 }
 
@@ -431,6 +483,7 @@ vox_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ 
                   const int32_t *__restrict__ voxel_num, int64_t max_rows, int P, int C, float *__restrict__ voxels,
                   int32_t *__restrict__ num_points)
 {
+    pdl_enter();
     int64_t t = (int64_t)blockIdx.x * VOX_THREADS + threadIdx.x;   // one thread per (pillar, slot)
     if (t >= max_rows * P) return;
     const int64_t m = t / P;
@@ -498,6 +551,7 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
     r.b.rows = a.take<char>((size_t)r.Q * c->max_points * ksz);
     r.b.pid_of_q = a.take<int32_t>((size_t)r.Q);
     r.b.bin_of_q = a.take<int32_t>((size_t)r.Q);
+    r.b.sat_of_q = a.take<uint8_t>((size_t)r.Q);
     r.b.q_of_point = a.take<int32_t>((size_t)n1);
     r.b.key_of_point = wide ? a.take<uint32_t>((size_t)n1) : nullptr;
     r.b.list = a.take<int32_t>((size_t)r.Q);
@@ -528,27 +582,27 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
     for (int r = 0; r < 2; ++r) fill_units += cv.ia.z_n[r];
     int init_blocks = (int)ceil_div(fill_units, 1024 * 4);
     init_blocks = init_blocks < 1 ? 1 : (init_blocks > 148 * 2 ? 148 * 2 : init_blocks);
-    vox_init_kernel<<<init_blocks + (WIDE ? 1 : 0), 1024, 0, st>>>(points, n, prm.C, WIDE ? 1 : 0, w.coarse, w.fine, cv.ia);
+    launch_pdl(vox_init_kernel, dim3(init_blocks + (WIDE ? 1 : 0)), dim3(1024), 0, st, points, n, prm.C, WIDE ? 1 : 0, w.coarse, w.fine, cv.ia);
     if (int rc = check_launch("vox_init_kernel")) return rc;
-    vox_scatter_kernel<K><<<nb, VOX_THREADS, 0, st>>>(points, n, prm, perm, w);
+    launch_pdl(vox_scatter_kernel<K>, dim3(nb), dim3(VOX_THREADS), 0, st, points, n, prm, perm, w);
     if (int rc = check_launch("vox_scatter_kernel")) return rc;
     const unsigned cap = 148 * 8;    // persistent-style grids: the cell count is only known on the device
     auto capped = [&](int64_t blocks) { return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap); };
-    vox_cell_prefix_kernel<K><<<capped(ceil_div(cv.Q, Q1_THREADS / 32)) / 4 + 1, Q1_THREADS, 0, st>>>(prm, w);
+    launch_pdl(vox_cell_prefix_kernel<K>, dim3(capped(ceil_div(cv.Q, Q1_THREADS / 32)) / 4 + 1), dim3(Q1_THREADS), 0, st, prm, w);
     if (int rc = check_launch("vox_cell_prefix_kernel")) return rc;
-    vox_bucket_kernel<K><<<capped(qb), VOX_THREADS, 0, st>>>(w);
+    launch_pdl(vox_bucket_kernel<K>, dim3(capped(qb)), dim3(VOX_THREADS), 0, st, w);
     if (int rc = check_launch("vox_bucket_kernel")) return rc;
-    vox_rank_kernel<K><<<capped(ceil_div(cv.Q, VOX_THREADS / 32)), VOX_THREADS, 0, st>>>(prm, w, coors, voxel_num, pillar_map);
+    launch_pdl(vox_rank_kernel<K>, dim3(capped(ceil_div(cv.Q, VOX_THREADS / 32))), dim3(VOX_THREADS), 0, st, prm, w, coors, voxel_num, pillar_map);
     if (int rc = check_launch("vox_rank_kernel")) return rc;
-    vox_place_kernel<K><<<nb, VOX_THREADS, 0, st>>>(n, prm, w);
+    launch_pdl(vox_place_kernel<K>, dim3((unsigned)(ceil_div(n, PLACE_THREADS) < 148 * 4 ? ceil_div(n, PLACE_THREADS) : 148 * 4)), dim3(PLACE_THREADS), 0, st, n, prm, w);
     if (int rc = check_launch("vox_place_kernel")) return rc;
     const int64_t slots = max_rows * prm.P;
     const unsigned gb = (unsigned)ceil_div(slots, VOX_THREADS);
     const bool vec4 = prm.vec4 && ((uintptr_t)voxels % 16 == 0);
     if (vec4)
-        vox_gather_kernel<K, true><<<gb, VOX_THREADS, 0, st>>>(points, perm, w, voxel_num, max_rows, prm.P, prm.C, voxels, num_points);
+        launch_pdl(vox_gather_kernel<K, true>, dim3(gb), dim3(VOX_THREADS), 0, st, points, perm, w, (const int32_t *)voxel_num, max_rows, prm.P, prm.C, voxels, num_points);
     else
-        vox_gather_kernel<K, false><<<gb, VOX_THREADS, 0, st>>>(points, perm, w, voxel_num, max_rows, prm.P, prm.C, voxels, num_points);
+        launch_pdl(vox_gather_kernel<K, false>, dim3(gb), dim3(VOX_THREADS), 0, st, points, perm, w, (const int32_t *)voxel_num, max_rows, prm.P, prm.C, voxels, num_points);
     return check_launch("vox_gather_kernel");
 }
 
@@ -622,8 +676,7 @@ extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *c
     q.vec4 = (q.C == 4 && ((uintptr_t)points % 16 == 0)) ? 1 : 0;
     int bits = 0;
     while (((int64_t)1 << bits) < n) ++bits;                 // positions < 2^bits
-    q.shift = bits > 6 ? bits - 6 : 0;                       // 64 chunks
-    q.fine_shift = bits > 9 ? bits - 9 : 0;                  // 512 fine bins
+    q.bits = bits;
 
     const int32_t *order_perm = order == PP_ORDER_PERM ? perm : nullptr;
     const int64_t max_rows = max_rows_of(n, cfg);
