@@ -37,7 +37,7 @@ WORKLOAD = "D1M tile (1e6 pts, 0.16 m pillars, 12000x32, 432x496 canvas, reflect
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
@@ -47,7 +47,7 @@ def parse():
 def base_config(n_gpus):
     return {"workload": WORKLOAD, "n_points": N_POINTS, "n_boxes": N_BOXES, "frames_per_step_per_gpu": 1,
             "nms": {"score_thr": NMS_SCORE_THR, "iou_thr": NMS_IOU_THR, "extent_m": NMS_EXTENT},
-            "parallelism": "frames sharded over %d GPU(s), no collective" % n_gpus,
+            "parallelism": "frames sharded over %d GPU(s), no collective; 4 independent frames in flight per GPU" % n_gpus,
             "l2": "inputs larger than L2: ring of %d tiles + %d canvases per GPU (%.0f MB)" %
                   (RING_TILES, RING_CANVAS, RING_TILES * 16.0 + RING_CANVAS * 54.85)}
 
@@ -200,7 +200,6 @@ def run_ours(args):
     d_boxes = [t.to(dev) for t in host_boxes]
     d_scores = [t.to(dev) for t in host_scores]
     pipe = pipeline.FramePipeline(geom, pfn, N_POINTS, device=dev)
-    pipe_given = pipeline.FramePipeline(geom, pfn, N_POINTS, order=_lib.ORDER_GIVEN, device=dev)
     nms = pipeline.NmsStage(N_BOXES, device=dev)
     canvases = [pipe.new_canvas() for _ in range(RING_CANVAS)]
     stream = torch.cuda.current_stream()
@@ -237,19 +236,82 @@ def run_ours(args):
     m_pillars = int(pipe.voxel_num.item())
     keep_n = int(nms.count.item())
 
-    # ---- headline: device-resident, K steps ----------------------------------------------------
+    # ---- frames in flight ----------------------------------------------------------------------
+    # Frames are independent, so the host keeps N_SLOTS frames in flight, each on its own stream with its own
+    # pipeline buffers: the single-CTA NMS sweep of one frame overlaps the grid-filling kernels of the others,
+    # and (e2e) the H2D copy of frame i+1 overlaps the kernels of frame i.  A slot is reused only after its
+    # stream has been synchronised, i.e. after that frame's results are complete (e2e: on the host).
+    N_SLOTS = 4
+    slots = []
+    for k in range(N_SLOTS):
+        sl = {"stream": torch.cuda.Stream(device=dev),
+              "pipe": pipeline.FramePipeline(geom, pfn, N_POINTS, device=dev),
+              "pipe_given": pipeline.FramePipeline(geom, pfn, N_POINTS, order=_lib.ORDER_GIVEN, device=dev),
+              "nms": pipeline.NmsStage(N_BOXES, device=dev),
+              "pts": torch.empty_like(d_pts[0]), "boxes": torch.empty_like(d_boxes[0]),
+              "scores": torch.empty_like(d_scores[0]), "canvas": canvases[k % RING_CANVAS],
+              "keep": torch.empty((N_BOXES,), dtype=torch.int64).pin_memory(),
+              "cnt": torch.empty((2,), dtype=torch.int32).pin_memory()}
+        slots.append(sl)
+    h2d = host_pts[0].numel() * 4 + host_boxes[0].numel() * 4 + host_scores[0].numel() * 4
+    d2h = N_BOXES * 8 + 8
+
+    def submit(i, mode):
+        sl, j = slots[i % N_SLOTS], i % RING_TILES
+        st = sl["stream"]
+        p = sl["pipe_given"] if mode == "given" else sl["pipe"]
+        with torch.cuda.stream(st):
+            if mode == "e2e":
+                sl["pts"].copy_(host_pts[j], non_blocking=True)
+                sl["boxes"].copy_(host_boxes[j], non_blocking=True)
+                sl["scores"].copy_(host_scores[j], non_blocking=True)
+                pts_, boxes_, scores_ = sl["pts"], sl["boxes"], sl["scores"]
+            else:
+                pts_, boxes_, scores_ = d_pts[j], d_boxes[j], d_scores[j]
+            p.run(pts_, sl["canvas"], st)
+            sl["nms"].run(boxes_, scores_, NMS_SCORE_THR, NMS_IOU_THR, 0, st)
+            if mode == "e2e":
+                sl["keep"].copy_(sl["nms"].keep, non_blocking=True)
+                sl["cnt"][0:1].copy_(sl["nms"].count, non_blocking=True)
+                sl["cnt"][1:2].copy_(p.voxel_num, non_blocking=True)
+
+    def run_in_flight(steps, mode):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for sl in slots:
+            sl["stream"].wait_stream(stream)
+        for i in range(steps):
+            if i >= N_SLOTS:
+                slots[i % N_SLOTS]["stream"].synchronize()      # frame i - N_SLOTS is complete
+            submit(i, mode)
+        for sl in slots:
+            sl["stream"].synchronize()
+            stream.wait_stream(sl["stream"])
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- headline: device-resident inputs, K frames, N_SLOTS in flight ---------------------------
+    run_in_flight(max(W, 2 * N_SLOTS), "resident")
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
                            os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
     l0 = _lib.launch_count()
-    ms_total = timed(step, K)
+    ms_total = run_in_flight(K, "resident")
     launches = _lib.launch_count() - l0
     clocks = sampler.stop()
     value = world * K / (ms_total * 1e-3)
+    # single stream, one frame at a time (latency view of the same step)
+    ms_serial = timed(step, min(K, 100))
 
     # ---- same, points pre-ordered (PP_ORDER_GIVEN: no reflectance sort) -------------------------
-    for i in range(3):
-        step(i, pipe_given)
-    ms_given = timed(lambda i: step(i, pipe_given), K)
+    run_in_flight(2 * N_SLOTS, "given")
+    ms_given = run_in_flight(K, "given")
 
     # ---- stage split (events around each stage, separate pass) ---------------------------------
     def split_pass(steps):
@@ -282,28 +344,15 @@ def run_ours(args):
             for k, (c, ms) in _lib.profile_report().items()}
 
     # ---- e2e: host buffers in, host results out, through the same C ABI -------------------------
-    stage_pts = torch.empty_like(d_pts[0])
-    stage_boxes, stage_scores = torch.empty_like(d_boxes[0]), torch.empty_like(d_scores[0])
-    out_keep = torch.empty((N_BOXES,), dtype=torch.int64).pin_memory()
-    out_cnt = torch.empty((2,), dtype=torch.int32).pin_memory()
-    h2d = host_pts[0].numel() * 4 + host_boxes[0].numel() * 4 + host_scores[0].numel() * 4
-    d2h = out_keep.numel() * 8 + 8
-
-    def e2e_step(i):
-        j = i % RING_TILES
-        stage_pts.copy_(host_pts[j], non_blocking=True)
-        stage_boxes.copy_(host_boxes[j], non_blocking=True)
-        stage_scores.copy_(host_scores[j], non_blocking=True)
-        pipe.run(stage_pts, canvases[i % RING_CANVAS], stream)
-        nms.run(stage_boxes, stage_scores, NMS_SCORE_THR, NMS_IOU_THR, 0, stream)
-        out_keep.copy_(nms.keep, non_blocking=True)
-        out_cnt[0:1].copy_(nms.count, non_blocking=True)
-        out_cnt[1:2].copy_(pipe.voxel_num, non_blocking=True)
-        stream.synchronize()           # the caller gets its frame's results before the next frame
-
-    for i in range(3):
-        e2e_step(i)
-    ms_e2e = timed(e2e_step, K)
+    run_in_flight(2 * N_SLOTS, "e2e")
+    # the host-buffer path must give the device-resident path's results (checked on tile 0)
+    submit(0, "e2e")
+    slots[0]["stream"].synchronize()
+    step(0)
+    torch.cuda.synchronize()
+    assert int(slots[0]["cnt"][0]) == int(nms.count.item()) and int(slots[0]["cnt"][1]) == int(pipe.voxel_num.item())
+    assert torch.equal(slots[0]["keep"][:int(slots[0]["cnt"][0])], nms.keep[:int(nms.count.item())].cpu())
+    ms_e2e = run_in_flight(K, "e2e")
     e2e_value = world * K / (ms_e2e * 1e-3)
 
     if rank != 0:
@@ -349,13 +398,15 @@ def run_ours(args):
     cpu = cpu_baseline(args.cpu_seconds) if world == 1 else None
     line = {"metric": "voxelize+scatter+NMS frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "frames_in_flight": N_SLOTS, "single_stream_ms_per_frame": ms_serial / min(K, 100),
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(base_config(world), pillars=m_pillars, nms_kept=keep_n),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K,
-                    "note": "pinned host points/boxes/scores -> H2D -> same C-ABI calls -> D2H keep list + counts, "
-                            "stream synchronised every frame; the canvas stays on the device for the backbone"},
+                    "note": "pinned host points/boxes/scores -> H2D -> same C-ABI calls -> D2H keep list + counts; "
+                            "%d frames in flight on %d streams, a frame's results are on the host before its slot is "
+                            "reused; the canvas stays on the device for the backbone" % (N_SLOTS, N_SLOTS)},
             "roofline": roofline, "cpu_baseline": cpu,
             "stages": stage_roof, "kernels": kern,
             "given_order": {"value": world * K / (ms_given * 1e-3), "unit": "frames/s", "ms_per_step": ms_given / K,
