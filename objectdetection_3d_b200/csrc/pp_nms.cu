@@ -78,6 +78,7 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
     const int i = row0 + t;
     if (i >= n) return;
     const float4 a = srect[i];
+    const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
 #pragma unroll 1
     for (int wd = 0; wd < MT_COLS / 64; ++wd) {
         const int c_start = col0 + wd * 64;
@@ -104,8 +105,26 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
         while (cand) {
             const int j = __ffsll((long long)cand) - 1;
             cand &= cand - 1;
-            // (remaining, selected) argument order of model/utils.py:412
-            if (rect_iou(s_col[wd * 64 + j], a, 0, 1e-6f) > thr) bits |= 1ull << j;
+            const float4 q = s_col[wd * 64 + j];
+            bool hit;
+            if (PREFILTER) {
+                // iou > thr  <=>  overlap > thr * union, decided without the division unless the two sides are
+                // within 1e-6 relative of each other (then the reference's exact IEEE quotient is evaluated)
+                float w = __fsub_rn(fminf(q.z, a.z), fmaxf(q.x, a.x));
+                float h = __fsub_rn(fminf(q.w, a.w), fmaxf(q.y, a.y));
+                w = w < 0.f ? 0.f : w;
+                h = h < 0.f ? 0.f : h;
+                const float ov = __fmul_rn(w, h);
+                // (remaining, selected) argument order of model/utils.py:412 -> area1 = column box
+                const float area_q = __fmul_rn(__fsub_rn(q.z, q.x), __fsub_rn(q.w, q.y));
+                const float uni = fmaxf(__fsub_rn(__fadd_rn(area_q, area_a), ov), 1e-6f);
+                const float tu = __fmul_rn(thr, uni);
+                hit = ov > __fmul_rn(tu, 1.000001f) && ov > 1e-30f;
+                if (!hit && ov >= __fmul_rn(tu, 0.999999f)) hit = __fdiv_rn(ov, uni) > thr;
+            } else {
+                hit = rect_iou(q, a, 0, 1e-6f) > thr;
+            }
+            if (hit) bits |= 1ull << j;
         }
         const int cw = c_start >> 6, kb = cw - (i >> 6);
         mask[(size_t)i * nw_stride + cw] = bits;
