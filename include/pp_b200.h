@@ -148,6 +148,11 @@ PP_API int pp_scatter_dense(const float *feat, const void *coors, int coors_kind
                      const int32_t *m_dev, int C, int batch_index, int B, int D, int H, int W,
                      float *canvas, void *map_ws, size_t map_ws_bytes, pp_stream_t stream);
 
+/* Same scatter, fed by the cell -> pillar map that pp_voxelize already produced (pillar_map argument):
+ * no map build, one kernel.  feat (M, C); pillar_map (B*D*H*W) int32 in (b, z, y, x) order, -1 = empty. */
+PP_API int pp_scatter_mapped(const float *feat, const int32_t *pillar_map, int C, int B, int D, int H, int W,
+                             float *canvas, pp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Stage 3 -- boxes: codec, corners, IoU, NMS.  Boxes are 9-parameter
  * [x, y, z_bottom, dx, dy, dz, rx, ry, rz] (config.yaml:5).

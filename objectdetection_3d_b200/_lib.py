@@ -46,6 +46,8 @@ SIGNATURES = {
     "pp_scatter_workspace_bytes": (_sz, [ctypes.c_int] * 4),
     "pp_scatter_dense": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _i64, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _sz, _vp]),
+    "pp_scatter_mapped": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         _vp, _vp]),
     "pp_box_encode": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pp_box_decode": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "pp_limit_period": (ctypes.c_int, [_vp, _i64, _f32, _f32, _vp, _vp]),

@@ -46,15 +46,26 @@ __device__ __forceinline__ void load_xy(const PillarIn &a, int64_t m, int &cx, i
     }
 }
 
-// Builds the decorated (P, C+5) row of pillar m in shared memory (row stride ld), one warp.
+// Builds the decorated (P, C+5) row of pillar m in shared memory (row stride ld), one warp.  The raw points are
+// staged into the row first (one coalesced read of the pillar), then decorated in place.
 __device__ void decorate_row(const PillarIn &a, int64_t m, int n, float *row, int ld, int lane)
 {
     const int P = a.P, C = a.C;
     const float *v = a.voxels + m * P * C;
+    if (C == 4 && ((reinterpret_cast<uintptr_t>(v) & 15) == 0)) {
+        for (int p = lane; p < P; p += 32) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(v) + p);
+            float *o = row + p * ld;
+            o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+        }
+    } else {
+        for (int i = lane; i < P * C; i += 32) row[(i / C) * ld + (i % C)] = __ldg(v + i);
+    }
+    __syncwarp();
     // mean over ALL P slots (zero padded), summed sequentially like the oracle (:493-494)
     float s = 0.f;
     if (lane < 3)
-        for (int p = 0; p < P; ++p) s = __fadd_rn(s, __ldg(v + p * C + lane));
+        for (int p = 0; p < P; ++p) s = __fadd_rn(s, row[p * ld + lane]);
     const float nf = (float)n;
     const float mean = __fdiv_rn(s, nf);
     const float mx_ = __shfl_sync(0xFFFFFFFFu, mean, 0);
@@ -67,11 +78,11 @@ __device__ void decorate_row(const PillarIn &a, int64_t m, int n, float *row, in
     for (int p = lane; p < P; p += 32) {
         const float mask = (n > p) ? 1.f : 0.f;                          // utils.py:456
         float *o = row + p * ld;
-        float x = __ldg(v + p * C), y = __ldg(v + p * C + 1), z = __ldg(v + p * C + 2);
+        const float x = o[0], y = o[1], z = o[2];
         o[0] = __fmul_rn(x, mask);
         o[1] = __fmul_rn(y, mask);
         o[2] = __fmul_rn(z, mask);
-        for (int k = 3; k < C; ++k) o[k] = __fmul_rn(__ldg(v + p * C + k), mask);
+        for (int k = 3; k < C; ++k) o[k] = __fmul_rn(o[k], mask);
         o[C + 0] = __fmul_rn(__fsub_rn(x, mx_), mask);                   // :496
         o[C + 1] = __fmul_rn(__fsub_rn(y, my_), mask);
         o[C + 2] = __fmul_rn(__fsub_rn(z, mz_), mask);
@@ -163,6 +174,7 @@ __global__ void __launch_bounds__(PIL_THREADS)
 pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const float *__restrict__ scale,
                        const float *__restrict__ shift, int U, float *__restrict__ out)
 {
+    pdl_enter();
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int P = a.P;
@@ -246,7 +258,7 @@ scatter_map_kernel(const CoorsIn c, int64_t M, const int32_t *__restrict__ m_dev
     atomicMax(map + (((int64_t)b * D + z) * H + y) * W + x, (int32_t)i);
 }
 
-constexpr int CANVAS_CELLS = 128;   // cells per CTA: 32 lanes x float4
+constexpr int CANVAS_CELLS = 128;   // cells per CTA pass: 32 lanes x float4
 constexpr int CANVAS_WARPS = 8;
 
 // Each CTA owns 128 consecutive cells of one (b, z) plane and writes all C channels of them.
@@ -255,6 +267,7 @@ __global__ void __launch_bounds__(CANVAS_WARPS * 32)
 scatter_canvas_kernel(const float *__restrict__ feat, const int32_t *__restrict__ map, int C, int D, int64_t HW,
                       int tiles_per_plane, float *__restrict__ canvas)
 {
+    pdl_enter();
     __shared__ int32_t s_pid[CANVAS_CELLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t plane = blockIdx.x / tiles_per_plane;        // b * D + z
@@ -377,11 +390,11 @@ extern "C" int pp_pillar_features(const float *voxels, const void *num_points, i
         const unsigned grid = pillar_grid(M);
         cudaStream_t st = (cudaStream_t)stream;
         switch (C + 5) {
-        case 8: pfn_fused_small_kernel<8><<<grid, PIL_THREADS, smem, st>>>(a, weight, scale, shift, U, feat); break;
-        case 9: pfn_fused_small_kernel<9><<<grid, PIL_THREADS, smem, st>>>(a, weight, scale, shift, U, feat); break;
-        case 10: pfn_fused_small_kernel<10><<<grid, PIL_THREADS, smem, st>>>(a, weight, scale, shift, U, feat); break;
-        case 11: pfn_fused_small_kernel<11><<<grid, PIL_THREADS, smem, st>>>(a, weight, scale, shift, U, feat); break;
-        default: pfn_fused_small_kernel<12><<<grid, PIL_THREADS, smem, st>>>(a, weight, scale, shift, U, feat); break;
+        case 8: launch_pdl(pfn_fused_small_kernel<8>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
+        case 9: launch_pdl(pfn_fused_small_kernel<9>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
+        case 10: launch_pdl(pfn_fused_small_kernel<10>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
+        case 11: launch_pdl(pfn_fused_small_kernel<11>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
+        default: launch_pdl(pfn_fused_small_kernel<12>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
         }
         return check_launch("pfn_fused_small_kernel");
     }
@@ -426,5 +439,26 @@ extern "C" int pp_scatter_dense(const float *feat, const void *coors, int coors_
         scatter_canvas_kernel<true><<<grid, CANVAS_WARPS * 32, 0, st>>>(feat, map, C, D, HW, (int)tiles_per_plane, canvas);
     else
         scatter_canvas_kernel<false><<<grid, CANVAS_WARPS * 32, 0, st>>>(feat, map, C, D, HW, (int)tiles_per_plane, canvas);
+    return check_launch("scatter_canvas_kernel");
+}
+
+extern "C" int pp_scatter_mapped(const float *feat, const int32_t *pillar_map, int C, int B, int D, int H, int W,
+                                 float *canvas, pp_stream_t stream)
+{
+    pp::enter((cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    PP_REQUIRE(C > 0 && B > 0 && D > 0 && H > 0 && W > 0, "bad shape");
+    PP_REQUIRE(feat && pillar_map && canvas, "null pointer");
+    const int64_t HW = (int64_t)H * W;
+    const int64_t tiles_per_plane = ceil_div(HW, CANVAS_CELLS);
+    PP_REQUIRE((int64_t)B * D * tiles_per_plane < (1ll << 31), "canvas too large");
+    const unsigned grid = (unsigned)((int64_t)B * D * tiles_per_plane);
+    const bool vec4 = (HW % 4 == 0) && ((uintptr_t)canvas % 16 == 0);
+    if (vec4)
+        launch_pdl(scatter_canvas_kernel<true>, dim3(grid), dim3(CANVAS_WARPS * 32), 0, st, feat, pillar_map, C, D, HW,
+                   (int)tiles_per_plane, canvas);
+    else
+        launch_pdl(scatter_canvas_kernel<false>, dim3(grid), dim3(CANVAS_WARPS * 32), 0, st, feat, pillar_map, C, D, HW,
+                   (int)tiles_per_plane, canvas);
     return check_launch("scatter_canvas_kernel");
 }

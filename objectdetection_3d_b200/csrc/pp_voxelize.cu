@@ -143,7 +143,7 @@ __device__ __forceinline__ u64 key_min(u64 *p, u64 v) { return atomicMin(p, v); 
 // One launch replaces the memsets: CTA 0 sorts the key sample (bitonic, shared memory) while the other CTAs
 // fill map = -1, the first `r_init` cell rows (cnt = 0, first = rows = +inf) and the small counters.
 struct InitArgs {
-    int4 *ff_ptr[3];  int64_t ff_n[3];     // regions filled with 0xFF (16-byte units)
+    int4 *ff_ptr[4];  int64_t ff_n[4];     // regions filled with 0xFF (16-byte units)
     int4 *z_ptr[2];   int64_t z_n[2];      // regions filled with 0
 };
 
@@ -157,7 +157,7 @@ vox_init_kernel(const float *__restrict__ points, int64_t n, int C, int wide, u6
         const int64_t nb = gridDim.x - (wide ? 1 : 0), b = blockIdx.x - (wide ? 1 : 0);
         const int4 ff = make_int4(-1, -1, -1, -1), zz = make_int4(0, 0, 0, 0);
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 4; ++r)
             for (int64_t i = b * 1024 + tid; i < ia.ff_n[r]; i += nb * 1024) ia.ff_ptr[r][i] = ff;
 #pragma unroll
         for (int r = 0; r < 2; ++r)
@@ -564,6 +564,7 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
     r.ia.ff_ptr[0] = (int4 *)r.b.map;    r.ia.ff_n[0] = units16(ff0_bytes);
     r.ia.ff_ptr[1] = (int4 *)r.b.first;  r.ia.ff_n[1] = units16((size_t)r_init * ksz);
     r.ia.ff_ptr[2] = (int4 *)r.b.rows;   r.ia.ff_n[2] = units16((size_t)r_init * c->max_points * ksz);
+    r.ia.ff_ptr[3] = nullptr;            r.ia.ff_n[3] = 0;      // optional pillar_map, set by the caller
     r.ia.z_ptr[0] = (int4 *)((char *)ws + z0_off);  r.ia.z_n[0] = units16(z0_bytes);
     r.ia.z_ptr[1] = (int4 *)r.b.cnt;     r.ia.z_n[1] = units16((size_t)r_init * NCHUNK * 4);
     return r;
@@ -578,7 +579,7 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
     const unsigned nb = (unsigned)ceil_div(n, VOX_THREADS);
     const unsigned qb = (unsigned)ceil_div(cv.Q, VOX_THREADS);
     int64_t fill_units = 0;
-    for (int r = 0; r < 3; ++r) fill_units += cv.ia.ff_n[r];
+    for (int r = 0; r < 4; ++r) fill_units += cv.ia.ff_n[r];
     for (int r = 0; r < 2; ++r) fill_units += cv.ia.z_n[r];
     int init_blocks = (int)ceil_div(fill_units, 1024 * 4);
     init_blocks = init_blocks < 1 ? 1 : (init_blocks > 148 * 2 ? 148 * 2 : init_blocks);
@@ -641,12 +642,9 @@ extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *c
     PP_REQUIRE(cfg->grid[0] > 0 && cfg->grid[1] > 0 && cfg->grid[2] > 0, "empty grid");
     const int64_t cells = (int64_t)cfg->grid[0] * cfg->grid[1] * cfg->grid[2];
     PP_REQUIRE(cells < (1ll << 31), "grid too large (>= 2^31 cells)");
-    if (pillar_map) {
-        PP_CUDA_TRY(cudaMemsetAsync(pillar_map, 0xFF, (size_t)cells * 4, st));
-        prof_mark("memset");
-    }
     if (n == 0 || cfg->max_voxels == 0) {
         PP_CUDA_TRY(cudaMemsetAsync(voxel_num, 0, sizeof(int32_t), st));
+        if (pillar_map) PP_CUDA_TRY(cudaMemsetAsync(pillar_map, 0xFF, (size_t)cells * 4, st));
         return PP_OK;
     }
     PP_REQUIRE(points && voxels && coors && num_points && workspace, "null pointer");
@@ -678,6 +676,15 @@ extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *c
     while (((int64_t)1 << bits) < n) ++bits;                 // positions < 2^bits
     q.bits = bits;
 
+    if (pillar_map) {          // filled with -1 by the init kernel (needs 16-byte alignment; else a memset)
+        if (((uintptr_t)pillar_map % 16 == 0) && (cells % 4 == 0)) {
+            cv.ia.ff_ptr[3] = (int4 *)pillar_map;
+            cv.ia.ff_n[3] = cells / 4;
+        } else {
+            PP_CUDA_TRY(cudaMemsetAsync(pillar_map, 0xFF, (size_t)cells * 4, st));
+            prof_mark("memset");
+        }
+    }
     const int32_t *order_perm = order == PP_ORDER_PERM ? perm : nullptr;
     const int64_t max_rows = max_rows_of(n, cfg);
     if (wide)

@@ -47,8 +47,8 @@ class FramePipeline:
         self.U = int(w.shape[0])
         assert w.shape[1] == self.C + 5
         self.feat = torch.empty((self.rows, self.U + 1), dtype=torch.float32, device=d)
-        self.sc_ws_bytes = int(self.lib.pp_scatter_workspace_bytes(1, self.D, self.H, self.W))
-        self.sc_ws = torch.empty((self.sc_ws_bytes,), dtype=torch.uint8, device=d)
+        # cell -> pillar map written by the voxelizer, consumed by the canvas kernel (no separate map build)
+        self.pillar_map = torch.empty((self.D, self.H, self.W), dtype=torch.int32, device=d)
         vx, vy = float(geom["voxel_size"][0]), float(geom["voxel_size"][1])
         self.vx, self.vy = vx, vy
         self.x_off = vx / 2 + geom["point_cloud_range"][0]
@@ -61,7 +61,7 @@ class FramePipeline:
         n = points.shape[0]
         assert n <= self.n_points and points.shape[1] == self.C
         _lib.check(self.lib.pp_voxelize(_ptr(points), n, ctypes.byref(self.cfg), self.order, None, _ptr(self.voxels),
-                                        _ptr(self.coors), _ptr(self.num), _ptr(self.voxel_num), None,
+                                        _ptr(self.coors), _ptr(self.num), _ptr(self.voxel_num), _ptr(self.pillar_map),
                                         _ptr(self.vox_ws), self.vox_ws_bytes, _sp(stream)))
 
     def encode_scatter(self, canvas, stream):
@@ -69,9 +69,8 @@ class FramePipeline:
             _ptr(self.voxels), _ptr(self.num), _lib.NUM_I32, _ptr(self.coors), _lib.COORS_XYZ_I32, self.rows,
             _ptr(self.voxel_num), self.P, self.C, self.vx, self.vy, self.x_off, self.y_off, _ptr(self.w),
             _ptr(self.scale), _ptr(self.shift), self.U, _ptr(self.feat), _sp(stream)))
-        _lib.check(self.lib.pp_scatter_dense(
-            _ptr(self.feat), _ptr(self.coors), _lib.COORS_XYZ_I32, self.rows, _ptr(self.voxel_num), self.U + 1, 0, 1,
-            self.D, self.H, self.W, _ptr(canvas), _ptr(self.sc_ws), self.sc_ws_bytes, _sp(stream)))
+        _lib.check(self.lib.pp_scatter_mapped(_ptr(self.feat), _ptr(self.pillar_map), self.U + 1, 1, self.D, self.H,
+                                              self.W, _ptr(canvas), _sp(stream)))
 
     def run(self, points, canvas, stream=None):
         stream = stream or torch.cuda.current_stream()

@@ -271,3 +271,32 @@ def test_head_golden(pp):
     assert np.array_equal(pi.cpu().numpy(), g["pos_idx"])
     assert np.array_equal(ni.cpu().numpy(), g["neg_idx"])
     assert_close_t1(ab.cpu().numpy(), g["assigned"], atol=1e-5, what="assigned")
+
+
+@pytest.mark.parametrize("order", ["reflectance", "given"])
+def test_frame_pipeline_full_size(pp, oracle, order):
+    """BASELINE configs[1] through the preallocated pipeline (voxelize -> PFN -> mapped scatter) vs the oracle."""
+    from objectdetection_3d_b200 import _lib, pipeline, synth
+    g, pfn = synth.G_KITTI, synth.pfn_params(9, 63, seed=5)
+    pts = synth.dense_tile()
+    pipe = pipeline.FramePipeline(g, pfn, len(pts),
+                                  order=_lib.ORDER_REFLECTANCE_DESC if order == "reflectance" else _lib.ORDER_GIVEN)
+    canvas = pipe.new_canvas()
+    for _ in range(2):          # twice: the workspace must be reusable without re-initialisation by the caller
+        pipe.run(cu(pts), canvas)
+    torch.cuda.synchronize()
+    m = int(pipe.voxel_num.item())
+    ov, oc, on = oracle.points_to_voxel(pts, np.array(g["voxel_size"], np.float32), np.array(g["point_cloud_range"]),
+                                        32, 12000, order == "reflectance")
+    assert m == len(ov)
+    assert np.array_equal(pipe.voxels[:m].cpu().numpy(), ov)
+    assert np.array_equal(pipe.coors[:m].cpu().numpy(), oc) and np.array_equal(pipe.num[:m].cpu().numpy(), on)
+    pm = pipe.pillar_map.cpu().numpy()
+    assert (pm >= 0).sum() == m and np.array_equal(pm[oc[:, 2], oc[:, 1], oc[:, 0]], np.arange(m))
+    coors4 = np.concatenate([np.zeros((m, 1), np.int64), oc[:, [2, 1, 0]].astype(np.int64)], 1)
+    feat = oracle.pillar_feature_net(ov, on, coors4, [pfn], g["voxel_size"], g["point_cloud_range"])
+    ref = oracle.scatter_dense(feat, coors4.astype(np.int32), 1, 1, pipe.H, pipe.W)
+    got = canvas.cpu().numpy()
+    scale = float(np.abs(pts[:, :3]).max())
+    assert_close_t1(got, ref, atol=1e-5 * scale * 4, what="canvas")
+    assert np.array_equal(got == 0, ref == 0) or np.abs(got[(got == 0) != (ref == 0)]).max() < 1e-4
