@@ -6,6 +6,8 @@
 //             64-step register chain, then all threads OR the kept rows into the running removed mask.
 // The IoU is evaluated exactly like bbox_iou2D (pp_boxes.cuh::rect_iou), so the keep set is identical
 // to the reference's greedy loop on the same rectangles.
+#include <cuda_fp16.h>
+
 #include "pp_boxes.cuh"
 #include "pp_common.cuh"
 #include "pp_sort.cuh"
@@ -58,6 +60,18 @@ constexpr int MT_COLS = 256;   // columns (remaining boxes) per CTA = 4 mask wor
 // Two phases per 64-column word: (1) a 4-compare interval test marks the columns whose rectangle
 // intersects the row's (a superset of the hits when thr >= 0); (2) only those columns get the exact
 // bbox_iou2D evaluation (rect_iou, IEEE division), so decisions equal the reference's `iou > thr`.
+// (x1, y1) rounded down and (x2, y2) rounded up to half precision, clamped to the finite half range
+__device__ __forceinline__ uint2 rect_to_half(const float4 r)
+{
+    const float L = 60000.f;
+    const __half2 lo = __halves2half2(__float2half_rd(fminf(fmaxf(r.x, -L), L)), __float2half_rd(fminf(fmaxf(r.y, -L), L)));
+    const __half2 hi = __halves2half2(__float2half_ru(fminf(fmaxf(r.z, -L), L)), __float2half_ru(fminf(fmaxf(r.w, -L), L)));
+    uint2 o;
+    o.x = *reinterpret_cast<const unsigned *>(&lo);
+    o.y = *reinterpret_cast<const unsigned *>(&hi);
+    return o;
+}
+
 template <bool PREFILTER>
 __global__ void __launch_bounds__(MT_ROWS)
 nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_cand, float thr, int nw_stride,
@@ -67,18 +81,23 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
     const int row0 = blockIdx.y * MT_ROWS, col0 = blockIdx.x * MT_COLS;
     if (row0 >= n || col0 >= n || col0 + MT_COLS <= row0) return;
     __shared__ float4 s_col[MT_COLS];
+    __shared__ uint2 s_colh[MT_COLS];     // the same rectangles as conservative half2 pairs: (x1,y1) down, (x2,y2) up
     const int t = threadIdx.x;
 #pragma unroll
     for (int k = 0; k < MT_COLS / MT_ROWS; ++k) {
         const int c = col0 + t + k * MT_ROWS;
         // out-of-range columns get an empty rectangle: never intersects
-        s_col[t + k * MT_ROWS] = c < n ? srect[c] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+        const float4 q = c < n ? srect[c] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+        s_col[t + k * MT_ROWS] = q;
+        s_colh[t + k * MT_ROWS] = rect_to_half(q);
     }
     __syncthreads();
     const int i = row0 + t;
     if (i >= n) return;
     const float4 a = srect[i];
     const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const uint2 ah = rect_to_half(a);
+    const __half2 a_lo = *reinterpret_cast<const __half2 *>(&ah.x), a_hi = *reinterpret_cast<const __half2 *>(&ah.y);
 #pragma unroll 1
     for (int wd = 0; wd < MT_COLS / 64; ++wd) {
         const int c_start = col0 + wd * 64;
@@ -86,16 +105,25 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
         if (c_start + 63 < i) continue;       // entirely below the diagonal: never read
         unsigned lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
         if (PREFILTER) {
+            // Phase 1 on packed halves: both components of (q_hi - a_lo) and (a_hi - q_lo) must be >= 0.  The
+            // halves are rounded outwards, so this marks a superset of the intersecting pairs with 2 HADD2 + 3
+            // integer ops per pair; phase 2 decides every marked pair exactly in fp32.
             lo = hi = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float4 q = s_col[wd * 64 + j];
-                if (q.z > a.x && a.z > q.x && q.w > a.y && a.w > q.y) lo |= 1u << j;
+                const uint2 qh = s_colh[wd * 64 + j];
+                const __half2 d1 = __hsub2(*reinterpret_cast<const __half2 *>(&qh.y), a_lo);
+                const __half2 d2 = __hsub2(a_hi, *reinterpret_cast<const __half2 *>(&qh.x));
+                const unsigned sg = (*reinterpret_cast<const unsigned *>(&d1) | *reinterpret_cast<const unsigned *>(&d2)) & 0x80008000u;
+                if (sg == 0) lo |= 1u << j;
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float4 q = s_col[wd * 64 + 32 + j];
-                if (q.z > a.x && a.z > q.x && q.w > a.y && a.w > q.y) hi |= 1u << j;
+                const uint2 qh = s_colh[wd * 64 + 32 + j];
+                const __half2 d1 = __hsub2(*reinterpret_cast<const __half2 *>(&qh.y), a_lo);
+                const __half2 d2 = __hsub2(a_hi, *reinterpret_cast<const __half2 *>(&qh.x));
+                const unsigned sg = (*reinterpret_cast<const unsigned *>(&d1) | *reinterpret_cast<const unsigned *>(&d2)) & 0x80008000u;
+                if (sg == 0) hi |= 1u << j;
             }
         }
         u64 cand = ((u64)hi << 32) | lo;
