@@ -17,6 +17,9 @@ namespace {
 
 typedef unsigned long long u64;
 constexpr int NMS_THREADS = 256;
+// device scalars of one pp_nms call
+enum { SC_N = 0, SC_N1 = 1, SC_K1 = 2, SC_N2 = 3, SC_TICKET = 4, SC_COUNT = 8 };
+constexpr int NMS_LEVEL1 = 2048;   // boxes resolved first; the rest is filtered against their keep set before its own NMS
 constexpr int SWEEP_THREADS = 1024;
 
 __global__ void __launch_bounds__(NMS_THREADS)
@@ -41,11 +44,13 @@ nms_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ sc
 }
 
 __global__ void __launch_bounds__(NMS_THREADS)
-nms_gather_kernel(const float4 *__restrict__ rect, const uint32_t *__restrict__ order, const int32_t *__restrict__ n_cand,
-                  float4 *__restrict__ srect)
+nms_gather_kernel(const float4 *__restrict__ rect, const uint32_t *__restrict__ order, int32_t *__restrict__ sc,
+                  float4 *__restrict__ srect, int level1)
 {
     int64_t r = (int64_t)blockIdx.x * NMS_THREADS + threadIdx.x;
-    if (r < *n_cand) srect[r] = rect[order[r]];
+    const int n = sc[SC_N];
+    if (r == 0) sc[SC_N1] = n < level1 ? n : level1;
+    if (r < n) srect[r] = rect[order[r]];
 }
 
 constexpr int SW_L = 7;                     // words after the diagonal handled by the sweep's resolver warp
@@ -175,7 +180,8 @@ __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" 
 __global__ void __launch_bounds__(SWEEP_THREADS)
 nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int nw_stride,
                  const int32_t *__restrict__ n_cand, const uint32_t *__restrict__ order, int64_t *__restrict__ keep,
-                 int32_t *__restrict__ keep_count, int nw_cap)
+                 const int32_t *__restrict__ keep_base, int32_t *__restrict__ keep_count,
+                 int32_t *__restrict__ kept_rank, int32_t *__restrict__ kept_n, int nw_cap)
 {
     extern __shared__ __align__(16) u64 sw_smem[];
     u64 *ring = sw_smem;                                   // [SW_RING][SW_L+1][64]
@@ -300,7 +306,8 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
     __syncthreads();
     __shared__ int s_warp_sum[SWEEP_THREADS / 32];
     __shared__ int s_base;
-    if (tid == 0) s_base = 0;
+    const int base0 = keep_base ? *keep_base : 0;      // keep entries of the previous level come first
+    if (tid == 0) s_base = base0;
     __syncthreads();
     for (int w0 = 0; w0 < nw; w0 += SWEEP_THREADS) {
         const int w = w0 + tid;
@@ -320,46 +327,164 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
         while (k) {
             const int i = __ffsll((long long)k) - 1;
             k &= k - 1;
+            if (kept_rank) kept_rank[pos - base0] = w * 64 + i;
             keep[pos++] = (int64_t)order[w * 64 + i];
         }
         __syncthreads();
         if (tid == SWEEP_THREADS - 1) s_base = pos;      // last thread holds the running total
         __syncthreads();
     }
-    if (tid == 0) *keep_count = s_base;
+    if (tid == 0) {
+        *keep_count = s_base;
+        if (kept_n) *kept_n = s_base - base0;
+    }
+}
+
+// Boxes below the first level that the first level's keep set does not suppress, compacted in rank order: they
+// only need NMS among themselves afterwards (every box above them has already been accounted for).
+constexpr uint32_t FLT_AGG = 1u << 30, FLT_PREFIX = 2u << 30, FLT_MASK = 3u << 30;
+
+constexpr int FLT_BOXES = 64;                       // boxes per CTA
+constexpr int FLT_SPLIT = NMS_THREADS / FLT_BOXES;  // threads that share one box (each scans 1/FLT_SPLIT of the keep set)
+
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__ order, int32_t *__restrict__ sc,
+                  const int32_t *__restrict__ kept_rank, float thr, float4 *__restrict__ srect2,
+                  uint32_t *__restrict__ order2, uint32_t *status)
+{
+    __shared__ float4 s_k[NMS_THREADS];
+    __shared__ uint32_t s_tile, s_excl;
+    __shared__ uint32_t s_warp[NMS_THREADS / 32];
+    __shared__ unsigned char s_dead[FLT_BOXES];
+    const int n = sc[SC_N], n1 = sc[SC_N1], k1 = sc[SC_K1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int num_tiles = (n - n1 + FLT_BOXES - 1) / FLT_BOXES;
+    if ((int)blockIdx.x >= num_tiles) return;
+    if (tid == 0) s_tile = atomicAdd((uint32_t *)&sc[SC_TICKET], 1u);
+    if (tid < FLT_BOXES) s_dead[tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int bi = tid / FLT_SPLIT, part = tid % FLT_SPLIT;      // box of this thread, its share of the keep set
+    const int r = n1 + (int)tile * FLT_BOXES + bi;
+    const bool valid = r < n;
+    const float4 box = valid ? srect[r] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+    const bool zero_hits = 0.f > thr;
+    bool dead = false;
+    for (int k0 = 0; k0 < k1; k0 += NMS_THREADS) {
+        if (k0 + tid < k1) s_k[tid] = srect[kept_rank[k0 + tid]];
+        __syncthreads();
+        const int kn = min(NMS_THREADS, k1 - k0);
+        if (valid && !dead) {
+            for (int j = part; j < kn; j += FLT_SPLIT) {
+                const float4 q = s_k[j];
+                // empty intersection -> iou == 0 exactly; otherwise bbox_iou2D with (remaining, selected) = (box, kept)
+                const bool apart = !(fminf(box.z, q.z) > fmaxf(box.x, q.x) && fminf(box.w, q.w) > fmaxf(box.y, q.y));
+                if (apart ? zero_hits : (rect_iou(box, q, 0, 1e-6f) > thr)) { dead = true; break; }
+            }
+        }
+        __syncthreads();
+    }
+    if (dead) s_dead[bi] = 1;
+    __syncthreads();
+    // ordered compaction: block scan of the survivor flags + decoupled look-back over the (ticket-ordered) tiles
+    const bool alive = tid < FLT_BOXES && (n1 + (int)tile * FLT_BOXES + tid) < n && !s_dead[tid];
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NMS_THREADS / 32; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < warp) wbase += c;
+        total += c;
+    }
+    if (tid == 0) {
+        uint32_t excl = 0;
+        if (tile == 0) {
+            atomicExch(status, FLT_PREFIX | total);
+        } else {
+            atomicExch(status + tile, FLT_AGG | total);
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                const uint32_t v = *((volatile uint32_t *)(status + t));
+                if ((v & FLT_MASK) == 0) continue;
+                excl += v & ~FLT_MASK;
+                if ((v & FLT_MASK) == FLT_PREFIX) break;
+                --t;
+            }
+            atomicExch(status + tile, FLT_PREFIX | (excl + total));
+        }
+        s_excl = excl;
+        if ((int)tile == num_tiles - 1) sc[SC_N2] = (int32_t)(excl + total);
+    }
+    __syncthreads();
+    if (alive) {
+        const int rr = n1 + (int)tile * FLT_BOXES + tid;
+        const uint32_t pos = s_excl + wbase + __popc(bal & lanemask_lt());
+        srect2[pos] = srect[rr];
+        order2[pos] = order[rr];
+    }
 }
 
 struct NmsWs {
-    int32_t *n_cand;
-    u64 *band;
+    int32_t *sc;
+    uint32_t *status;          // look-back state of the filter's compaction
+    u64 *band1, *band2;
     size_t zero_bytes;
-    float4 *rect, *srect;
-    uint32_t *keys, *keys_sorted, *order;
-    u64 *mask;
+    float4 *rect, *srect, *srect2;
+    uint32_t *keys, *keys_sorted, *order, *order2;
+    int32_t *kept_rank;
+    u64 *mask1, *mask2;
     void *sort_ws;
     size_t sort_ws_bytes;
-    int nw;
+    int nw1, nw2;
 };
 
 NmsWs carve(void *ws, int64_t N, size_t *total)
 {
     NmsWs w;
-    int64_t n1 = N > 0 ? N : 1;
-    w.nw = (int)ceil_div(n1, 64);
+    const int64_t n1 = N > 0 ? N : 1;
+    const int64_t l1 = n1 < NMS_LEVEL1 ? n1 : NMS_LEVEL1;
+    const int64_t l2 = n1 > NMS_LEVEL1 ? n1 - NMS_LEVEL1 : 0;
+    w.nw1 = (int)ceil_div(l1, 64);
+    w.nw2 = (int)ceil_div(l2 > 0 ? l2 : 1, 64);
     Arena a(ws, (size_t)-1);
-    w.n_cand = a.take<int32_t>(64);
-    w.band = a.take<u64>((size_t)w.nw * SW_BAND);
+    w.sc = a.take<int32_t>(64);
+    w.status = a.take<uint32_t>((size_t)ceil_div(l2 > 0 ? l2 : 1, FLT_BOXES));
+    w.band1 = a.take<u64>((size_t)w.nw1 * SW_BAND);
+    w.band2 = a.take<u64>(l2 > 0 ? (size_t)w.nw2 * SW_BAND : 1);
     w.zero_bytes = a.off;
     w.rect = a.take<float4>((size_t)n1);
     w.srect = a.take<float4>((size_t)n1);
+    w.srect2 = a.take<float4>((size_t)(l2 > 0 ? l2 : 1));
     w.keys = a.take<uint32_t>((size_t)n1);
     w.keys_sorted = a.take<uint32_t>((size_t)n1);
     w.order = a.take<uint32_t>((size_t)n1);
-    w.mask = a.take<u64>((size_t)n1 * w.nw);
+    w.order2 = a.take<uint32_t>((size_t)(l2 > 0 ? l2 : 1));
+    w.kept_rank = a.take<int32_t>((size_t)l1);
+    w.mask1 = a.take<u64>((size_t)l1 * w.nw1);
+    w.mask2 = a.take<u64>(l2 > 0 ? (size_t)l2 * w.nw2 : 1);
     w.sort_ws_bytes = sort_workspace_bytes(n1);
     w.sort_ws = a.take<char>(w.sort_ws_bytes);
     *total = align_up(a.off);
     return w;
+}
+
+int launch_level(const float4 *rects, const int32_t *n_ptr, int64_t n_max, float thr, int nw, u64 *mask, u64 *band,
+                 const uint32_t *order, int64_t *keep, const int32_t *keep_base, int32_t *keep_count,
+                 int32_t *kept_rank, int32_t *kept_n, cudaStream_t st)
+{
+    dim3 grid((unsigned)ceil_div(n_max, MT_COLS), (unsigned)ceil_div(n_max, MT_ROWS));
+    if (thr >= 0.f)      // a non-intersecting pair has iou == 0, which only exceeds a negative threshold
+        nms_mask_kernel<true><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band);
+    else
+        nms_mask_kernel<false><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band);
+    if (int rc = check_launch("nms_mask_kernel")) return rc;
+    const size_t smem = ((size_t)SW_RING * SW_BAND + 3 * (size_t)nw) * sizeof(u64) + (size_t)nw * sizeof(int);
+    PP_REQUIRE(smem <= 96 * 1024, "too many boxes for the sweep's shared memory");
+    nms_sweep_kernel<<<1, SWEEP_THREADS, smem, st>>>(mask, band, nw, n_ptr, order, keep, keep_base, keep_count, kept_rank,
+                                                     kept_n, nw);
+    return check_launch("nms_sweep_kernel");
 }
 
 }  // namespace
@@ -394,27 +519,30 @@ extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_st
         set_error("nms workspace too small: %zu < %zu", workspace_bytes, total);
         return PP_ERR_WORKSPACE;
     }
-    PP_CUDA_TRY(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));     // candidate count + diagonal band
+    PP_CUDA_TRY(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));     // scalars, look-back state, diagonal bands
     prof_mark("memset");
-    const unsigned nb = (unsigned)ceil_div(N, NMS_THREADS);
-    nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.n_cand);
-    if (int rc = check_launch("nms_prepare_kernel")) return rc;
-    if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st)) return rc;
-    nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.n_cand, w.srect);
-    if (int rc = check_launch("nms_gather_kernel")) return rc;
-    dim3 grid((unsigned)ceil_div(N, MT_COLS), (unsigned)ceil_div(N, MT_ROWS));
-    if (iou_thr >= 0.f)      // a non-intersecting pair has iou == 0, which only exceeds a negative threshold
-        nms_mask_kernel<true><<<grid, MT_ROWS, 0, st>>>(w.srect, w.n_cand, iou_thr, w.nw, w.mask, w.band);
-    else
-        nms_mask_kernel<false><<<grid, MT_ROWS, 0, st>>>(w.srect, w.n_cand, iou_thr, w.nw, w.mask, w.band);
-    if (int rc = check_launch("nms_mask_kernel")) return rc;
-    size_t smem = ((size_t)SW_RING * SW_BAND + 3 * (size_t)w.nw) * sizeof(u64) + (size_t)w.nw * sizeof(int);
     static bool attr_set = false;
     if (!attr_set) {
         PP_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    PP_REQUIRE(smem <= 96 * 1024, "too many boxes for the sweep's shared memory");
-    nms_sweep_kernel<<<1, SWEEP_THREADS, smem, st>>>(w.mask, w.band, w.nw, w.n_cand, w.order, keep, keep_count, w.nw);
-    return check_launch("nms_sweep_kernel");
+    const unsigned nb = (unsigned)ceil_div(N, NMS_THREADS);
+    nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.sc + SC_N);
+    if (int rc = check_launch("nms_prepare_kernel")) return rc;
+    if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st)) return rc;
+    nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.sc, w.srect, NMS_LEVEL1);
+    if (int rc = check_launch("nms_gather_kernel")) return rc;
+    // level 1: greedy NMS of the NMS_LEVEL1 best-scored candidates
+    const int64_t l1 = N < NMS_LEVEL1 ? N : NMS_LEVEL1;
+    if (int rc = launch_level(w.srect, w.sc + SC_N1, l1, iou_thr, w.nw1, w.mask1, w.band1, w.order, keep, nullptr,
+                              keep_count, w.kept_rank, w.sc + SC_K1, st))
+        return rc;
+    if (N <= NMS_LEVEL1) return PP_OK;
+    // the other candidates: drop those suppressed by level 1's keep set, compact in rank order, NMS among themselves
+    const int64_t l2 = N - NMS_LEVEL1;
+    nms_filter_kernel<<<(unsigned)ceil_div(l2, FLT_BOXES), NMS_THREADS, 0, st>>>(w.srect, w.order, w.sc, w.kept_rank,
+                                                                                    iou_thr, w.srect2, w.order2, w.status);
+    if (int rc = check_launch("nms_filter_kernel")) return rc;
+    return launch_level(w.srect2, w.sc + SC_N2, l2, iou_thr, w.nw2, w.mask2, w.band2, w.order2, keep, w.sc + SC_K1,
+                        keep_count, nullptr, nullptr, st);
 }
