@@ -46,6 +46,7 @@ struct VoxParams {
     int regime;   // 0: all f32   1: sub f32, div f64   2: all f64   (numba promotion)
     int P, max_voxels, C;
     int vec4;     // C == 4 and 16-byte aligned rows: float4 loads
+    int ticket;   // max_points <= 64: untruncated windows are filled in arrival order and sorted by the gather kernel
     int bits;     // 32-bit keys: positions < 2^bits; chunks / fine bins are geometric in the position (geo_bin)
 };
 
@@ -62,6 +63,7 @@ struct VoxBuf {
     int32_t *pid_of_q;     // [Q]
     int32_t *bin_of_q;     // [Q]
     uint8_t *sat_of_q;     // [Q] first chunk whose inclusive prefix reaches max_points (NCHUNK if none)
+    uint8_t *tick;         // [N] arrival index of the point inside its (cell, chunk), saturated at 255
     int32_t *q_of_point;   // [N]
     uint32_t *key_of_point;  // [N] primary key (64-bit mode only)
     int32_t *hist, *fill;  // [NFINE] each
@@ -268,7 +270,8 @@ vox_scatter_kernel(const float *__restrict__ points, int64_t n, const VoxParams 
     w.q_of_point[p] = q;
     K *first = (K *)w.first + q;
     if (key < __ldcg(first)) key_min(first, key);                // most points do not lower the minimum (L2 read, not .sys)
-    atomicAdd(w.cnt + (size_t)q * NCHUNK + ch, 1);
+    const int t = atomicAdd(w.cnt + (size_t)q * NCHUNK + ch, 1);
+    w.tick[p] = (uint8_t)(t < 255 ? t : 255);
 }
 
 // ---- Q1..Q3: per occupied cell --------------------------------------------------------------------------------
@@ -440,38 +443,86 @@ __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, con
     __syncthreads();
     const K cutoff = *(const K *)w.cutoff;
     const int P = prm.P;
-    for (int64_t p = (int64_t)blockIdx.x * PLACE_THREADS + threadIdx.x; p < n; p += (int64_t)gridDim.x * PLACE_THREADS) {
-        const int q = w.q_of_point[p];
-        if (q < 0) continue;
-        K key;
-        int ch;
-        if (WIDE) {
-            key = (K)(((u64)w.key_of_point[p] << 32) | (uint32_t)p);
-            ch = upper_bound_u64(s_coarse, NCHUNK - 1, (u64)key);
-        } else {
-            key = (K)(uint32_t)p;
-            ch = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
+    // Four points per thread and iteration: their loads, and later their insertion chains, are issued back to back
+    // (an in-order warp stalls at the first use of a result, so one point at a time would serialise every L2 round
+    // trip of the chain).
+    constexpr int IT = 4;
+    const int64_t stride = (int64_t)gridDim.x * PLACE_THREADS;
+    for (int64_t p0 = (int64_t)blockIdx.x * PLACE_THREADS + threadIdx.x; p0 < n; p0 += stride * IT) {
+        int q[IT], tk[IT];
+        uint32_t prim[IT];
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            const int64_t p = p0 + k * stride;
+            q[k] = p < n ? w.q_of_point[p] : -1;
+            tk[k] = p < n ? (int)w.tick[p] : 0;
+            prim[k] = (WIDE && p < n) ? w.key_of_point[p] : 0u;
         }
-        const int sat = q < PLACE_TABLE ? (int)s_sat[q] : (int)w.sat_of_q[q];
-        if (ch > sat) continue;                              // the pillar is full before this chunk (:303)
-        if (key >= cutoff) continue;                         // at or after the break: dropped
-        const int32_t *incl = w.cnt + (size_t)q * NCHUNK;
-        const int base = ch ? incl[ch - 1] : 0;
-        const int end = incl[ch];
-        const int wend = end < P ? end : P;
-        K *row = (K *)w.rows + (size_t)q * P;
-        if (end - base == 1) {                               // alone in its window: the slot is known
-            row[base] = key;
-            continue;
+        K key[IT];
+        int ch[IT], base[IT], end[IT];
+        bool act[IT];
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            const int64_t p = p0 + k * stride;
+            act[k] = q[k] >= 0;
+            base[k] = end[k] = 0;
+            key[k] = 0;
+            ch[k] = 0;
+            if (!act[k]) continue;
+            if (WIDE) {
+                key[k] = (K)(((u64)prim[k] << 32) | (uint32_t)p);
+                ch[k] = upper_bound_u64(s_coarse, NCHUNK - 1, (u64)key[k]);
+            } else {
+                key[k] = (K)(uint32_t)p;
+                ch[k] = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
+            }
+            const int sat = q[k] < PLACE_TABLE ? (int)s_sat[q[k]] : (int)w.sat_of_q[q[k]];
+            // full before this chunk (:303), or at / after the break
+            if (ch[k] > sat || key[k] >= cutoff) { act[k] = false; continue; }
+            const int32_t *incl = w.cnt + (size_t)q[k] * NCHUNK;
+            base[k] = ch[k] ? incl[ch[k] - 1] : 0;
+            end[k] = incl[ch[k]];
         }
-        // a few points share the window [base, wend): sorted insertion with a lock-free atomicMin chain.  Slots only
-        // decrease, every displaced key is pushed one slot down, so the final window is sorted for any interleaving.
-        if (__ldcg(row + wend - 1) < key) continue;              // the (truncated) window already holds smaller keys
-        K carry = key;
-        for (int k = base; k < wend; ++k) {
-            const K old = key_min(row + k, carry);
-            if (old == KeyInf<K>::value()) break;
-            carry = old > carry ? old : carry;
+        K *slot[IT];
+        K carry[IT];
+        int left[IT];
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            slot[k] = nullptr;
+            carry[k] = key[k];
+            left[k] = 0;
+            if (!act[k]) continue;
+            const int wend = end[k] < P ? end[k] : P;
+            K *row = (K *)w.rows + (size_t)q[k] * P;
+            if (end[k] - base[k] == 1) {                     // alone in its window: the slot is known
+                row[base[k]] = key[k];
+                act[k] = false;
+                continue;
+            }
+            if (prm.ticket && end[k] <= P) {                 // the whole window is kept: arrival order now, the
+                row[base[k] + tk[k]] = key[k];               // gather kernel sorts the row
+                act[k] = false;
+                continue;
+            }
+            // truncated window (more points than free slots): skip keys that can no longer enter it
+            if (wend < end[k] && __ldcg(row + wend - 1) < key[k]) { act[k] = false; continue; }
+            slot[k] = row + base[k];
+            left[k] = wend - base[k];
+        }
+        // A few points share a window: sorted insertion with a lock-free atomicMin chain.  Slots only decrease and
+        // every displaced key is pushed one slot down, so the final window is sorted for any interleaving.
+        while (act[0] || act[1] || act[2] || act[3]) {
+            K old[IT];
+#pragma unroll
+            for (int k = 0; k < IT; ++k)
+                if (act[k]) old[k] = key_min(slot[k], carry[k]);
+#pragma unroll
+            for (int k = 0; k < IT; ++k) {
+                if (!act[k]) continue;
+                if (old[k] == KeyInf<K>::value() || --left[k] == 0) { act[k] = false; continue; }
+                carry[k] = old[k] > carry[k] ? old[k] : carry[k];
+                ++slot[k];
+            }
         }
     }
 }
@@ -504,6 +555,83 @@ vox_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ 
         reinterpret_cast<float4 *>(voxels)[t] = v;
     } else {
         for (int c = 0; c < C; ++c) voxels[t * C + c] = valid ? __ldg(points + idx * C + c) : 0.f;
+    }
+}
+
+// P <= 64: one warp per pillar.  The row's keys (windows are in order, the keys inside a window are not) are sorted
+// in registers with a bitonic network, then lane s writes slot s.
+template <typename K>
+__device__ __forceinline__ K shfl_xor_key(K v, int m)
+{
+    if (sizeof(K) == 8) {
+        unsigned lo = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)v, m), hi = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)((u64)v >> 32), m);
+        return (K)(((u64)hi << 32) | lo);
+    }
+    return (K)__shfl_xor_sync(0xFFFFFFFFu, (unsigned)v, m);
+}
+
+template <typename K, bool TWO>
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_gather_sorted_kernel(const float *__restrict__ points, const int32_t *__restrict__ perm, const VoxBuf w,
+                         const int32_t *__restrict__ voxel_num, int P, int C, int vec4, float *__restrict__ voxels,
+                         int32_t *__restrict__ num_points)
+{
+    pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int nvox = *voxel_num;
+    for (int m = blockIdx.x * (VOX_THREADS / 32) + (threadIdx.x >> 5); m < nvox; m += gridDim.x * (VOX_THREADS / 32)) {
+        const K *row = (const K *)w.rows + (size_t)w.q_of_pid[m] * P;
+        K k0 = lane < P ? row[lane] : KeyInf<K>::value();
+        K k1 = (TWO && lane + 32 < P) ? row[lane + 32] : KeyInf<K>::value();
+        // bitonic sort of 32 (or 64) keys, element index e = r * 32 + lane
+#pragma unroll
+        for (int size = 2; size <= (TWO ? 64 : 32); size <<= 1) {
+#pragma unroll
+            for (int j = size >> 1; j > 0; j >>= 1) {
+                if (j == 32) {
+                    // partner is the other register of the same lane; e & size == 0 for both (size == 64): ascending
+                    const K lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
+                    k0 = lo; k1 = hi;
+                } else {
+                    const bool upper = (lane & j) != 0;
+                    {
+                        const K o = shfl_xor_key<K>(k0, j);
+                        const bool asc = (lane & size) == 0;             // e = lane for register 0
+                        const bool take_min = asc != upper;
+                        k0 = take_min ? (k0 < o ? k0 : o) : (k0 < o ? o : k0);
+                    }
+                    if (TWO) {
+                        const K o = shfl_xor_key<K>(k1, j);
+                        const bool asc = ((lane + 32) & size) == 0;      // e = lane + 32 for register 1
+                        const bool take_min = asc != upper;
+                        k1 = take_min ? (k1 < o ? k1 : o) : (k1 < o ? o : k1);
+                    }
+                }
+            }
+        }
+        const unsigned v0 = __ballot_sync(0xFFFFFFFFu, k0 != KeyInf<K>::value());
+        const unsigned v1 = TWO ? __ballot_sync(0xFFFFFFFFu, k1 != KeyInf<K>::value()) : 0u;
+        if (lane == 0) num_points[m] = __popc(v0) + __popc(v1);
+#pragma unroll
+        for (int r = 0; r < (TWO ? 2 : 1); ++r) {
+            const int s = lane + 32 * r;
+            if (s >= P) continue;
+            const K key = r ? k1 : k0;
+            const bool valid = key != KeyInf<K>::value();
+            int64_t idx = 0;
+            if (valid) {
+                const uint32_t pos = (uint32_t)key;                  // low word = position / original index
+                idx = perm ? (int64_t)(uint32_t)perm[pos] : (int64_t)pos;
+            }
+            const int64_t t = (int64_t)m * P + s;
+            if (vec4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) v = __ldg(reinterpret_cast<const float4 *>(points) + idx);
+                reinterpret_cast<float4 *>(voxels)[t] = v;
+            } else {
+                for (int c = 0; c < C; ++c) voxels[t * C + c] = valid ? __ldg(points + idx * C + c) : 0.f;
+            }
+        }
     }
 }
 
@@ -553,6 +681,7 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
     r.b.bin_of_q = a.take<int32_t>((size_t)r.Q);
     r.b.sat_of_q = a.take<uint8_t>((size_t)r.Q);
     r.b.q_of_point = a.take<int32_t>((size_t)n1);
+    r.b.tick = a.take<uint8_t>((size_t)n1);
     r.b.key_of_point = wide ? a.take<uint32_t>((size_t)n1) : nullptr;
     r.b.list = a.take<int32_t>((size_t)r.Q);
     r.b.lkey = a.take<char>((size_t)r.Q * ksz);
@@ -595,11 +724,21 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
     if (int rc = check_launch("vox_bucket_kernel")) return rc;
     launch_pdl(vox_rank_kernel<K>, dim3(capped(ceil_div(cv.Q, VOX_THREADS / 32))), dim3(VOX_THREADS), 0, st, prm, w, coors, voxel_num, pillar_map);
     if (int rc = check_launch("vox_rank_kernel")) return rc;
-    launch_pdl(vox_place_kernel<K>, dim3((unsigned)(ceil_div(n, PLACE_THREADS) < 148 * 4 ? ceil_div(n, PLACE_THREADS) : 148 * 4)), dim3(PLACE_THREADS), 0, st, n, prm, w);
+    launch_pdl(vox_place_kernel<K>, dim3((unsigned)(ceil_div(n, PLACE_THREADS * 4) < 148 * 4 ? ceil_div(n, PLACE_THREADS * 4) : 148 * 4)), dim3(PLACE_THREADS), 0, st, n, prm, w);
     if (int rc = check_launch("vox_place_kernel")) return rc;
+    const bool vec4 = prm.vec4 && ((uintptr_t)voxels % 16 == 0);
+    if (prm.ticket) {
+        const unsigned gs = (unsigned)(ceil_div(max_rows, VOX_THREADS / 32) < 148 * 8 ? ceil_div(max_rows, VOX_THREADS / 32) : 148 * 8);
+        if (prm.P <= 32)
+            launch_pdl(vox_gather_sorted_kernel<K, false>, dim3(gs), dim3(VOX_THREADS), 0, st, points, perm, w,
+                       (const int32_t *)voxel_num, prm.P, prm.C, vec4 ? 1 : 0, voxels, num_points);
+        else
+            launch_pdl(vox_gather_sorted_kernel<K, true>, dim3(gs), dim3(VOX_THREADS), 0, st, points, perm, w,
+                       (const int32_t *)voxel_num, prm.P, prm.C, vec4 ? 1 : 0, voxels, num_points);
+        return check_launch("vox_gather_sorted_kernel");
+    }
     const int64_t slots = max_rows * prm.P;
     const unsigned gb = (unsigned)ceil_div(slots, VOX_THREADS);
-    const bool vec4 = prm.vec4 && ((uintptr_t)voxels % 16 == 0);
     if (vec4)
         launch_pdl(vox_gather_kernel<K, true>, dim3(gb), dim3(VOX_THREADS), 0, st, points, perm, w, (const int32_t *)voxel_num, max_rows, prm.P, prm.C, voxels, num_points);
     else
@@ -675,6 +814,7 @@ extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *c
     int bits = 0;
     while (((int64_t)1 << bits) < n) ++bits;                 // positions < 2^bits
     q.bits = bits;
+    q.ticket = q.P <= 64 ? 1 : 0;
 
     if (pillar_map) {          // filled with -1 by the init kernel (needs 16-byte alignment; else a memset)
         if (((uintptr_t)pillar_map % 16 == 0) && (cells % 4 == 0)) {
