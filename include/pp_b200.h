@@ -177,6 +177,10 @@ enum { PP_IOU = 0, PP_IOF = 1, PP_GIOU = 2 };
  * so results are bit-identical to the eager torch ops on identical rectangles. */
 PP_API int pp_bbox_iou2d(const float *b1, int64_t m, const float *b2, int64_t n, int mode, float eps,
                   float *out, pp_stream_t stream);
+/* Rotated BEV IoU (extension named by the north star; the reference has no rotated-rectangle IoU, its nms_dim == 2
+ * form is the AABB above).  Footprint of a 9-parameter box = centre (x,y), size (dx,dy), yaw rz; (m,9),(n,9) -> (m,n).
+ * Sutherland-Hodgman clipping on the FP32 CUDA cores; checked against a float64 oracle (tests/test_rotated_iou.py). */
+PP_API int pp_iou_rotated_bev(const float *b1, int64_t m, const float *b2, int64_t n, float *out, pp_stream_t stream);
 /* iou_jit, ops/ops_numba.py:7-36 (eps added to widths, evaluated in f64 like numba) */
 PP_API int pp_iou_jit(const float *boxes, int64_t N, const float *query, int64_t K, double eps, float *out,
                pp_stream_t stream);
@@ -188,10 +192,20 @@ PP_API int pp_iou_jit(const float *boxes, int64_t N, const float *query, int64_t
  * scores: element i at scores[i * score_stride].
  * keep (N) int64: kept ORIGINAL indices in descending-score order; keep_count device int32 scalar.
  */
+enum { PP_NMS_AABB2D = 0, PP_NMS_ROT_BEV = 1 };
 PP_API size_t pp_nms_workspace_bytes(int64_t N);
 PP_API int pp_nms(const float *boxes9, const float *scores, int64_t score_stride, int64_t N, float score_thr,
            float iou_thr, int64_t *keep, int32_t *keep_count, void *workspace, size_t workspace_bytes,
            pp_stream_t stream);
+
+/* Same greedy NMS with a selectable pair test.  PP_NMS_AABB2D = pp_nms (the reference's nms_dim == 2 form);
+ * PP_NMS_ROT_BEV = rotated BEV footprints (x, y, dx, dy, rz) with the pair IoU of pp_iou_rotated_bev (extension named
+ * by the north star, no counterpart in the reference): the footprints' bounding rectangles drive the tile prefilter,
+ * polygon clipping runs on the FP32 cores only for pairs whose rectangles overlap. */
+PP_API size_t pp_nms_workspace_bytes_mode(int64_t N, int iou_mode);
+PP_API int pp_nms_mode(const float *boxes9, const float *scores, int64_t score_stride, int64_t N, float score_thr,
+                float iou_thr, int iou_mode, int64_t *keep, int32_t *keep_count, void *workspace,
+                size_t workspace_bytes, pp_stream_t stream);
 
 /* Stable radix sort of (u32 key, u32 value) pairs, ascending; building block exposed for tests. */
 PP_API size_t pp_sort_workspace_bytes(int64_t n);

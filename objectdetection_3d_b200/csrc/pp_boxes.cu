@@ -123,6 +123,27 @@ iou2d_kernel(const float *__restrict__ b1, int64_t m, const float *__restrict__ 
     }
 }
 
+// (m,n) rotated BEV IoU: one thread per column box (staged in shared memory), 32 rows per CTA
+__global__ void __launch_bounds__(BX_THREADS)
+iou_rot_kernel(const float *__restrict__ b1, int64_t m, const float *__restrict__ b2, int64_t n, float *__restrict__ out)
+{
+    __shared__ RRect s_row[32];
+    const int64_t i0 = (int64_t)blockIdx.y * 32;
+    if (threadIdx.x < 32 && i0 + threadIdx.x < m) s_row[threadIdx.x] = rrect_from_box9(b1 + (i0 + threadIdx.x) * 9);
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;
+    if (j >= n) return;
+    const RRect q = rrect_from_box9(b2 + j * 9);
+    const float4 qa = rrect_aabb(q);
+    for (int r = 0; r < 32 && i0 + r < m; ++r) {
+        const RRect a = s_row[r];
+        const float4 aa = rrect_aabb(a);
+        float v = 0.f;
+        if (fminf(aa.z, qa.z) > fmaxf(aa.x, qa.x) && fminf(aa.w, qa.w) > fmaxf(aa.y, qa.y)) v = rrect_iou(a, q);
+        out[(i0 + r) * n + j] = v;
+    }
+}
+
 __global__ void __launch_bounds__(BX_THREADS)
 iou_jit_kernel(const float *__restrict__ boxes, int64_t N, const float *__restrict__ query, int64_t K, double eps,
                float *__restrict__ out)
@@ -247,4 +268,16 @@ extern "C" int pp_iou_jit(const float *boxes, int64_t N, const float *query, int
     PP_REQUIRE((uintptr_t)boxes % 16 == 0 && (uintptr_t)query % 16 == 0, "boxes must be 16-byte aligned");
     iou_jit_kernel<<<GRID1(N * K)>>>(boxes, N, query, K, eps, out);
     return check_launch("iou_jit_kernel");
+}
+
+extern "C" int pp_iou_rotated_bev(const float *b1, int64_t m, const float *b2, int64_t n, float *out, pp_stream_t stream)
+{
+    pp::enter((cudaStream_t)stream);
+    PP_REQUIRE(m >= 0 && n >= 0, "negative size");
+    if (m == 0 || n == 0) return PP_OK;
+    PP_REQUIRE(b1 && b2 && out, "null pointer");
+    PP_REQUIRE(ceil_div(m, 32) < 65536, "too many rows for one launch");
+    dim3 grid((unsigned)ceil_div(n, BX_THREADS), (unsigned)ceil_div(m, 32));
+    iou_rot_kernel<<<grid, BX_THREADS, 0, (cudaStream_t)stream>>>(b1, m, b2, n, out);
+    return check_launch("iou_rot_kernel");
 }

@@ -105,4 +105,89 @@ __device__ __forceinline__ float rect_iou(const float4 a, const float4 b, int mo
     return __fsub_rn(iou, __fdiv_rn(__fsub_rn(ea, uni), ea));
 }
 
+// ---- rotated BEV rectangles (extension: the north star's "rotated BEV IoU"; not in the reference) -----------------
+// BEV footprint of a 9-parameter box: centre (x, y), size (dx, dy), yaw rz.
+struct RRect {
+    float cx, cy, hx, hy, c, s;
+};
+
+__device__ __forceinline__ RRect rrect_from_box9(const float *b)
+{
+    RRect r;
+    r.cx = b[0]; r.cy = b[1];
+    r.hx = 0.5f * b[3]; r.hy = 0.5f * b[4];
+    sincosf(b[8], &r.s, &r.c);
+    return r;
+}
+
+// axis-aligned bounding rectangle of the footprint (conservative pre-filter for the pair tests)
+__device__ __forceinline__ float4 rrect_aabb(const RRect &r)
+{
+    const float ex = fabsf(r.c) * r.hx + fabsf(r.s) * r.hy, ey = fabsf(r.s) * r.hx + fabsf(r.c) * r.hy;
+    return make_float4(r.cx - ex, r.cy - ey, r.cx + ex, r.cy + ey);
+}
+
+// Area of the intersection of two rotated rectangles: Sutherland-Hodgman clipping of a's corners against the four
+// half-planes of b, evaluated in b's frame (where b is axis-aligned), then the shoelace formula.  FP32 CUDA cores.
+__device__ __forceinline__ float rrect_inter_area(const RRect &a, const RRect &b)
+{
+    float px[8], py[8], qx[8], qy[8];
+    const float sx[4] = {-1.f, 1.f, 1.f, -1.f}, sy[4] = {-1.f, -1.f, 1.f, 1.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float wx = a.cx + a.c * sx[i] * a.hx - a.s * sy[i] * a.hy - b.cx;
+        const float wy = a.cy + a.s * sx[i] * a.hx + a.c * sy[i] * a.hy - b.cy;
+        px[i] = b.c * wx + b.s * wy;
+        py[i] = -b.s * wx + b.c * wy;
+    }
+    int n = 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool yaxis = e >= 2;
+        const float sgn = (e & 1) ? -1.f : 1.f, lim = yaxis ? b.hy : b.hx;
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const int j = (i + 1 == n) ? 0 : i + 1;
+            const float ci = sgn * (yaxis ? py[i] : px[i]) - lim, cj = sgn * (yaxis ? py[j] : px[j]) - lim;
+            if (ci <= 0.f) { qx[m] = px[i]; qy[m] = py[i]; ++m; }
+            if ((ci < 0.f && cj > 0.f) || (ci > 0.f && cj < 0.f)) {
+                const float t = ci / (ci - cj);
+                qx[m] = px[i] + t * (px[j] - px[i]);
+                qy[m] = py[i] + t * (py[j] - py[i]);
+                ++m;
+            }
+        }
+        n = m;
+        for (int i = 0; i < n; ++i) { px[i] = qx[i]; py[i] = qy[i]; }
+    }
+    float area = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        area += px[i] * py[j] - px[j] * py[i];
+    }
+    return 0.5f * fabsf(area);
+}
+
+// Symmetric by construction: the pair is put into a canonical order before clipping, so iou(a,b) == iou(b,a)
+// bit for bit (the NMS decision must not depend on which box is "selected" and which "remaining").
+__device__ __forceinline__ float rrect_iou(const RRect &a, const RRect &b)
+{
+    const bool swap = (a.cx > b.cx) || (a.cx == b.cx && (a.cy > b.cy || (a.cy == b.cy && (a.hx > b.hx ||
+                      (a.hx == b.hx && (a.hy > b.hy || (a.hy == b.hy && a.s > b.s)))))));
+    const float inter = swap ? rrect_inter_area(b, a) : rrect_inter_area(a, b);
+    const float aa = 4.f * a.hx * a.hy, ab = 4.f * b.hx * b.hy;
+    const float uni = (swap ? ab + aa : aa + ab) - inter;
+    return inter / fmaxf(uni, 1e-6f);
+}
+
+// RRect <-> (float4, float2) for 16/8-byte loads and stores
+__device__ __forceinline__ float4 rrect_lo(const RRect &r) { return make_float4(r.cx, r.cy, r.hx, r.hy); }
+__device__ __forceinline__ float2 rrect_hi(const RRect &r) { return make_float2(r.c, r.s); }
+__device__ __forceinline__ RRect rrect_pack(const float4 lo, const float2 hi)
+{
+    RRect r;
+    r.cx = lo.x; r.cy = lo.y; r.hx = lo.z; r.hy = lo.w; r.c = hi.x; r.s = hi.y;
+    return r;
+}
+
 }  // namespace pp

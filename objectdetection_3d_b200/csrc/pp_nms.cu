@@ -24,7 +24,8 @@ constexpr int SWEEP_THREADS = 1024;
 
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, int64_t stride, int64_t N,
-                   float score_thr, float4 *__restrict__ rect, uint32_t *__restrict__ keys, int32_t *__restrict__ n_cand)
+                   float score_thr, float4 *__restrict__ rect, uint32_t *__restrict__ keys, int32_t *__restrict__ n_cand,
+                   float4 *__restrict__ rr_lo, float2 *__restrict__ rr_hi)
 {
     int64_t i = (int64_t)blockIdx.x * NMS_THREADS + threadIdx.x;
     bool cand = false;
@@ -32,9 +33,17 @@ nms_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ sc
         float b[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) b[k] = boxes[i * 9 + k];
-        float c[8][3];
-        box_corners(b, c);
-        rect[i] = corners_to_rect(c);
+        if (rr_lo) {
+            // PP_NMS_ROT_BEV: rotated footprint (x, y, dx, dy, rz); its bounding rectangle drives the prefilter
+            const RRect r = rrect_from_box9(b);
+            rect[i] = rrect_aabb(r);
+            rr_lo[i] = rrect_lo(r);
+            rr_hi[i] = rrect_hi(r);
+        } else {
+            float c[8][3];
+            box_corners(b, c);
+            rect[i] = corners_to_rect(c);
+        }
         float s = scores[i * stride];
         cand = s > score_thr;
         keys[i] = cand ? ~ordered_bits(s) : 0xFFFFFFFFu;
@@ -45,12 +54,17 @@ nms_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ sc
 
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_gather_kernel(const float4 *__restrict__ rect, const uint32_t *__restrict__ order, int32_t *__restrict__ sc,
-                  float4 *__restrict__ srect, int level1)
+                  float4 *__restrict__ srect, int level1, const float4 *__restrict__ rr_lo,
+                  const float2 *__restrict__ rr_hi, float4 *__restrict__ srr_lo, float2 *__restrict__ srr_hi)
 {
     int64_t r = (int64_t)blockIdx.x * NMS_THREADS + threadIdx.x;
     const int n = sc[SC_N];
     if (r == 0) sc[SC_N1] = n < level1 ? n : level1;
-    if (r < n) srect[r] = rect[order[r]];
+    if (r < n) {
+        const uint32_t o = order[r];
+        srect[r] = rect[o];
+        if (rr_lo) { srr_lo[r] = rr_lo[o]; srr_hi[r] = rr_hi[o]; }
+    }
 }
 
 constexpr int SW_L = 7;                     // words after the diagonal handled by the sweep's resolver warp
@@ -77,16 +91,19 @@ __device__ __forceinline__ uint2 rect_to_half(const float4 r)
     return o;
 }
 
-template <bool PREFILTER>
+template <bool PREFILTER, int MODE>
 __global__ void __launch_bounds__(MT_ROWS)
 nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_cand, float thr, int nw_stride,
-                u64 *__restrict__ mask, u64 *__restrict__ band)
+                u64 *__restrict__ mask, u64 *__restrict__ band, const float4 *__restrict__ srr_lo,
+                const float2 *__restrict__ srr_hi)
 {
     const int n = *n_cand;
     const int row0 = blockIdx.y * MT_ROWS, col0 = blockIdx.x * MT_COLS;
     if (row0 >= n || col0 >= n || col0 + MT_COLS <= row0) return;
     __shared__ float4 s_col[MT_COLS];
     __shared__ uint2 s_colh[MT_COLS];     // the same rectangles as conservative half2 pairs: (x1,y1) down, (x2,y2) up
+    __shared__ float4 s_rlo[MODE == PP_NMS_ROT_BEV ? MT_COLS : 1];     // rotated footprints of the column boxes
+    __shared__ float2 s_rhi[MODE == PP_NMS_ROT_BEV ? MT_COLS : 1];
     const int t = threadIdx.x;
 #pragma unroll
     for (int k = 0; k < MT_COLS / MT_ROWS; ++k) {
@@ -95,12 +112,18 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
         const float4 q = c < n ? srect[c] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
         s_col[t + k * MT_ROWS] = q;
         s_colh[t + k * MT_ROWS] = rect_to_half(q);
+        if (MODE == PP_NMS_ROT_BEV && c < n) {
+            s_rlo[t + k * MT_ROWS] = srr_lo[c];
+            s_rhi[t + k * MT_ROWS] = srr_hi[c];
+        }
     }
     __syncthreads();
     const int i = row0 + t;
     if (i >= n) return;
     const float4 a = srect[i];
     const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    RRect ra;
+    if (MODE == PP_NMS_ROT_BEV) ra = rrect_pack(srr_lo[i], srr_hi[i]);
     const uint2 ah = rect_to_half(a);
     const __half2 a_lo = *reinterpret_cast<const __half2 *>(&ah.x), a_hi = *reinterpret_cast<const __half2 *>(&ah.y);
 #pragma unroll 1
@@ -140,7 +163,14 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
             cand &= cand - 1;
             const float4 q = s_col[wd * 64 + j];
             bool hit;
-            if (PREFILTER) {
+            if (MODE == PP_NMS_ROT_BEV) {
+                // same definition as pp_iou_rotated_bev: 0 unless the fp32 bounding rectangles overlap, else the
+                // clipped-polygon IoU (symmetric in its arguments)
+                float v = 0.f;
+                if (fminf(a.z, q.z) > fmaxf(a.x, q.x) && fminf(a.w, q.w) > fmaxf(a.y, q.y))
+                    v = rrect_iou(rrect_pack(s_rlo[wd * 64 + j], s_rhi[wd * 64 + j]), ra);
+                hit = v > thr;
+            } else if (PREFILTER) {
                 // iou > thr  <=>  overlap > thr * union, decided without the division unless the two sides are
                 // within 1e-6 relative of each other (then the reference's exact IEEE quotient is evaluated)
                 float w = __fsub_rn(fminf(q.z, a.z), fmaxf(q.x, a.x));
@@ -347,12 +377,16 @@ constexpr uint32_t FLT_AGG = 1u << 30, FLT_PREFIX = 2u << 30, FLT_MASK = 3u << 3
 constexpr int FLT_BOXES = 64;                       // boxes per CTA
 constexpr int FLT_SPLIT = NMS_THREADS / FLT_BOXES;  // threads that share one box (each scans 1/FLT_SPLIT of the keep set)
 
+template <int MODE>
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__ order, int32_t *__restrict__ sc,
                   const int32_t *__restrict__ kept_rank, float thr, float4 *__restrict__ srect2,
-                  uint32_t *__restrict__ order2, uint32_t *status)
+                  uint32_t *__restrict__ order2, uint32_t *status, const float4 *__restrict__ srr_lo,
+                  const float2 *__restrict__ srr_hi, float4 *__restrict__ srr2_lo, float2 *__restrict__ srr2_hi)
 {
     __shared__ float4 s_k[NMS_THREADS];
+    __shared__ float4 s_klo[MODE == PP_NMS_ROT_BEV ? NMS_THREADS : 1];
+    __shared__ float2 s_khi[MODE == PP_NMS_ROT_BEV ? NMS_THREADS : 1];
     __shared__ uint32_t s_tile, s_excl;
     __shared__ uint32_t s_warp[NMS_THREADS / 32];
     __shared__ unsigned char s_dead[FLT_BOXES];
@@ -368,10 +402,16 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
     const int r = n1 + (int)tile * FLT_BOXES + bi;
     const bool valid = r < n;
     const float4 box = valid ? srect[r] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+    RRect rbox;
+    if (MODE == PP_NMS_ROT_BEV && valid) rbox = rrect_pack(srr_lo[r], srr_hi[r]);
     const bool zero_hits = 0.f > thr;
     bool dead = false;
     for (int k0 = 0; k0 < k1; k0 += NMS_THREADS) {
-        if (k0 + tid < k1) s_k[tid] = srect[kept_rank[k0 + tid]];
+        if (k0 + tid < k1) {
+            const int kr = kept_rank[k0 + tid];
+            s_k[tid] = srect[kr];
+            if (MODE == PP_NMS_ROT_BEV) { s_klo[tid] = srr_lo[kr]; s_khi[tid] = srr_hi[kr]; }
+        }
         __syncthreads();
         const int kn = min(NMS_THREADS, k1 - k0);
         if (valid && !dead) {
@@ -379,7 +419,11 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
                 const float4 q = s_k[j];
                 // empty intersection -> iou == 0 exactly; otherwise bbox_iou2D with (remaining, selected) = (box, kept)
                 const bool apart = !(fminf(box.z, q.z) > fmaxf(box.x, q.x) && fminf(box.w, q.w) > fmaxf(box.y, q.y));
-                if (apart ? zero_hits : (rect_iou(box, q, 0, 1e-6f) > thr)) { dead = true; break; }
+                bool hit;
+                if (apart) hit = zero_hits;
+                else if (MODE == PP_NMS_ROT_BEV) hit = rrect_iou(rbox, rrect_pack(s_klo[j], s_khi[j])) > thr;
+                else hit = rect_iou(box, q, 0, 1e-6f) > thr;
+                if (hit) { dead = true; break; }
             }
         }
         __syncthreads();
@@ -423,6 +467,7 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
         const uint32_t pos = s_excl + wbase + __popc(bal & lanemask_lt());
         srect2[pos] = srect[rr];
         order2[pos] = order[rr];
+        if (MODE == PP_NMS_ROT_BEV) { srr2_lo[pos] = srr_lo[rr]; srr2_hi[pos] = srr_hi[rr]; }
     }
 }
 
@@ -434,13 +479,15 @@ struct NmsWs {
     float4 *rect, *srect, *srect2;
     uint32_t *keys, *keys_sorted, *order, *order2;
     int32_t *kept_rank;
+    float4 *rr_lo, *srr_lo, *srr2_lo;      // PP_NMS_ROT_BEV only
+    float2 *rr_hi, *srr_hi, *srr2_hi;
     u64 *mask1, *mask2;
     void *sort_ws;
     size_t sort_ws_bytes;
     int nw1, nw2;
 };
 
-NmsWs carve(void *ws, int64_t N, size_t *total)
+NmsWs carve(void *ws, int64_t N, int mode, size_t *total)
 {
     NmsWs w;
     const int64_t n1 = N > 0 ? N : 1;
@@ -462,6 +509,13 @@ NmsWs carve(void *ws, int64_t N, size_t *total)
     w.order = a.take<uint32_t>((size_t)n1);
     w.order2 = a.take<uint32_t>((size_t)(l2 > 0 ? l2 : 1));
     w.kept_rank = a.take<int32_t>((size_t)l1);
+    const bool rot = mode == PP_NMS_ROT_BEV;
+    w.rr_lo = rot ? a.take<float4>((size_t)n1) : nullptr;
+    w.srr_lo = rot ? a.take<float4>((size_t)n1) : nullptr;
+    w.srr2_lo = rot ? a.take<float4>((size_t)(l2 > 0 ? l2 : 1)) : nullptr;
+    w.rr_hi = rot ? a.take<float2>((size_t)n1) : nullptr;
+    w.srr_hi = rot ? a.take<float2>((size_t)n1) : nullptr;
+    w.srr2_hi = rot ? a.take<float2>((size_t)(l2 > 0 ? l2 : 1)) : nullptr;
     w.mask1 = a.take<u64>((size_t)l1 * w.nw1);
     w.mask2 = a.take<u64>(l2 > 0 ? (size_t)l2 * w.nw2 : 1);
     w.sort_ws_bytes = sort_workspace_bytes(n1);
@@ -472,13 +526,19 @@ NmsWs carve(void *ws, int64_t N, size_t *total)
 
 int launch_level(const float4 *rects, const int32_t *n_ptr, int64_t n_max, float thr, int nw, u64 *mask, u64 *band,
                  const uint32_t *order, int64_t *keep, const int32_t *keep_base, int32_t *keep_count,
-                 int32_t *kept_rank, int32_t *kept_n, cudaStream_t st)
+                 int32_t *kept_rank, int32_t *kept_n, const float4 *rr_lo, const float2 *rr_hi, cudaStream_t st)
 {
     dim3 grid((unsigned)ceil_div(n_max, MT_COLS), (unsigned)ceil_div(n_max, MT_ROWS));
-    if (thr >= 0.f)      // a non-intersecting pair has iou == 0, which only exceeds a negative threshold
-        nms_mask_kernel<true><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band);
+    // thr >= 0: a pair whose bounding rectangles are apart has iou == 0, which only exceeds a negative threshold
+    if (rr_lo) {
+        if (thr >= 0.f)
+            nms_mask_kernel<true, PP_NMS_ROT_BEV><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, rr_lo, rr_hi);
+        else
+            nms_mask_kernel<false, PP_NMS_ROT_BEV><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, rr_lo, rr_hi);
+    } else if (thr >= 0.f)
+        nms_mask_kernel<true, PP_NMS_AABB2D><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, nullptr, nullptr);
     else
-        nms_mask_kernel<false><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band);
+        nms_mask_kernel<false, PP_NMS_AABB2D><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, nullptr, nullptr);
     if (int rc = check_launch("nms_mask_kernel")) return rc;
     const size_t smem = ((size_t)SW_RING * SW_BAND + 3 * (size_t)nw) * sizeof(u64) + (size_t)nw * sizeof(int);
     PP_REQUIRE(smem <= 96 * 1024, "too many boxes for the sweep's shared memory");
@@ -492,21 +552,24 @@ int launch_level(const float4 *rects, const int32_t *n_ptr, int64_t n_max, float
 
 using namespace pp;
 
-extern "C" size_t pp_nms_workspace_bytes(int64_t N)
+extern "C" size_t pp_nms_workspace_bytes_mode(int64_t N, int iou_mode)
 {
     size_t total;
-    carve(nullptr, N, &total);
+    carve(nullptr, N, iou_mode, &total);
     return total;
 }
 
-extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_stride, int64_t N, float score_thr,
-                      float iou_thr, int64_t *keep, int32_t *keep_count, void *workspace, size_t workspace_bytes,
-                      pp_stream_t stream)
+extern "C" size_t pp_nms_workspace_bytes(int64_t N) { return pp_nms_workspace_bytes_mode(N, PP_NMS_AABB2D); }
+
+extern "C" int pp_nms_mode(const float *boxes9, const float *scores, int64_t score_stride, int64_t N, float score_thr,
+                           float iou_thr, int iou_mode, int64_t *keep, int32_t *keep_count, void *workspace,
+                           size_t workspace_bytes, pp_stream_t stream)
 {
     pp::enter((cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     PP_REQUIRE(keep_count, "null keep_count");
     PP_REQUIRE(N >= 0 && N <= 131072, "N must be in [0, 131072]");
+    PP_REQUIRE(iou_mode == PP_NMS_AABB2D || iou_mode == PP_NMS_ROT_BEV, "unknown iou_mode");
     if (N == 0) {
         PP_CUDA_TRY(cudaMemsetAsync(keep_count, 0, sizeof(int32_t), st));
         return PP_OK;
@@ -514,7 +577,7 @@ extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_st
     PP_REQUIRE(boxes9 && scores && keep && workspace, "null pointer");
     PP_REQUIRE(score_stride >= 1, "bad score stride");
     size_t total;
-    NmsWs w = carve(workspace, N, &total);
+    NmsWs w = carve(workspace, N, iou_mode, &total);
     if (workspace_bytes < total) {
         set_error("nms workspace too small: %zu < %zu", workspace_bytes, total);
         return PP_ERR_WORKSPACE;
@@ -527,22 +590,38 @@ extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_st
         attr_set = true;
     }
     const unsigned nb = (unsigned)ceil_div(N, NMS_THREADS);
-    nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.sc + SC_N);
+    nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.sc + SC_N,
+                                                   w.rr_lo, w.rr_hi);
     if (int rc = check_launch("nms_prepare_kernel")) return rc;
     if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st)) return rc;
-    nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.sc, w.srect, NMS_LEVEL1);
+    nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.sc, w.srect, NMS_LEVEL1, w.rr_lo, w.rr_hi, w.srr_lo,
+                                                  w.srr_hi);
     if (int rc = check_launch("nms_gather_kernel")) return rc;
     // level 1: greedy NMS of the NMS_LEVEL1 best-scored candidates
     const int64_t l1 = N < NMS_LEVEL1 ? N : NMS_LEVEL1;
     if (int rc = launch_level(w.srect, w.sc + SC_N1, l1, iou_thr, w.nw1, w.mask1, w.band1, w.order, keep, nullptr,
-                              keep_count, w.kept_rank, w.sc + SC_K1, st))
+                              keep_count, w.kept_rank, w.sc + SC_K1, w.srr_lo, w.srr_hi, st))
         return rc;
     if (N <= NMS_LEVEL1) return PP_OK;
     // the other candidates: drop those suppressed by level 1's keep set, compact in rank order, NMS among themselves
     const int64_t l2 = N - NMS_LEVEL1;
-    nms_filter_kernel<<<(unsigned)ceil_div(l2, FLT_BOXES), NMS_THREADS, 0, st>>>(w.srect, w.order, w.sc, w.kept_rank,
-                                                                                    iou_thr, w.srect2, w.order2, w.status);
+    const unsigned fb = (unsigned)ceil_div(l2, FLT_BOXES);
+    if (iou_mode == PP_NMS_ROT_BEV)
+        nms_filter_kernel<PP_NMS_ROT_BEV><<<fb, NMS_THREADS, 0, st>>>(w.srect, w.order, w.sc, w.kept_rank, iou_thr, w.srect2,
+                                                                       w.order2, w.status, w.srr_lo, w.srr_hi, w.srr2_lo,
+                                                                       w.srr2_hi);
+    else
+        nms_filter_kernel<PP_NMS_AABB2D><<<fb, NMS_THREADS, 0, st>>>(w.srect, w.order, w.sc, w.kept_rank, iou_thr, w.srect2,
+                                                                      w.order2, w.status, nullptr, nullptr, nullptr, nullptr);
     if (int rc = check_launch("nms_filter_kernel")) return rc;
     return launch_level(w.srect2, w.sc + SC_N2, l2, iou_thr, w.nw2, w.mask2, w.band2, w.order2, keep, w.sc + SC_K1,
-                        keep_count, nullptr, nullptr, st);
+                        keep_count, nullptr, nullptr, w.srr2_lo, w.srr2_hi, st);
+}
+
+extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_stride, int64_t N, float score_thr,
+                      float iou_thr, int64_t *keep, int32_t *keep_count, void *workspace, size_t workspace_bytes,
+                      pp_stream_t stream)
+{
+    return pp_nms_mode(boxes9, scores, score_stride, N, score_thr, iou_thr, PP_NMS_AABB2D, keep, keep_count, workspace,
+                       workspace_bytes, stream);
 }

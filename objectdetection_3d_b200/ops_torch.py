@@ -48,6 +48,19 @@ def bbox_iou2D(bboxes1, bboxes2, mode='iou', eps=1e-6):
     return out
 
 
+def bbox_iou_rotated_bev(bboxes1, bboxes2):
+    """Extension (north star "rotated BEV IoU"): IoU of the rotated BEV footprints (x, y, dx, dy, rz) of two sets of
+    9-parameter boxes, (m,9),(n,9) -> (m,n).  Not part of the reference (its nms_dim == 2 path is the AABB form)."""
+    assert bboxes1.size(-1) == 9 and bboxes2.size(-1) == 9
+    b1, b2 = _f32c(bboxes1), _f32c(bboxes2)
+    m, n = b1.shape[0], b2.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=b1.device)
+    if m * n == 0:
+        return out
+    _lib.check(_lib.load().pp_iou_rotated_bev(_ptr(b1), m, _ptr(b2), n, _ptr(out), _stream()))
+    return out
+
+
 def box3d_overlap(boxes1, boxes2, eps=1e-2):
     """ops/ops_torch.py:711-755 (pytorch3d oriented 3-D IoU).  Out of the pinned scope: SURVEY.md
     section 8(f) rank 1 ("next"); the reference's own implementation lives in an absent third-party

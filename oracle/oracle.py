@@ -252,3 +252,12 @@ def grid_anchors(featmap_size, anchor_range, sizes, rotations):
     lib().ppo_grid_anchors(_p(rg, c_f32p), _p(sz, c_f32p), sz.shape[0], _p(rt, c_f32p), rt.shape[0],
                            D, H, W, _p(out, c_f32p))
     return out
+
+
+def bbox_iou_rotated_bev(b1, b2):
+    """Rotated BEV IoU of 9-parameter boxes (footprint x, y, dx, dy, rz), float64.  Extension, see pp_oracle.c."""
+    b1, b2 = _f32(b1), _f32(b2)
+    out = np.empty((b1.shape[0], b2.shape[0]), dtype=np.float64)
+    lib().ppo_iou_rotated_bev(_p(b1, c_f32p), ctypes.c_int64(b1.shape[0]), _p(b2, c_f32p), ctypes.c_int64(b2.shape[0]),
+                              _p(out, c_f64p))
+    return out

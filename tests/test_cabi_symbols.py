@@ -52,7 +52,9 @@ def test_argument_validation_without_gpu(lib):
     assert lib.pp_voxelize_max_rows(500, ctypes.byref(cfg)) == 500
     assert lib.pp_voxelize_workspace_bytes(1_000_000, ctypes.byref(cfg), 1) > \
         lib.pp_voxelize_workspace_bytes(1_000_000, ctypes.byref(cfg), 0) > 4_000_000
-    assert lib.pp_nms_workspace_bytes(20000) >= 20000 * 313 * 8
+    # two-level NMS: a 2048^2 bitmask for the best boxes + a (N-2048)^2 one for the filtered rest
+    assert lib.pp_nms_workspace_bytes(20000) >= (2048 * 32 + 17952 * 281) * 8
+    assert lib.pp_nms_workspace_bytes_mode(20000, 1) > lib.pp_nms_workspace_bytes_mode(20000, 0) == lib.pp_nms_workspace_bytes(20000)
     # invalid arguments are rejected before any CUDA call
     rc = lib.pp_voxelize(None, 10, ctypes.byref(cfg), 7, None, None, None, None, ctypes.c_void_p(8), None, None, 0, None)
     assert rc == _lib.PP_ERR_INVALID and b"order" in lib.pp_last_error()
