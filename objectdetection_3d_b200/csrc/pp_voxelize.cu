@@ -10,17 +10,18 @@
 //   `break`     = the (max_voxels+1)-th smallest cell minimum is the cutoff: keys >= cutoff are dropped,
 //   slot        = rank of the key inside its cell, capped at max_points.
 //
-// Kernels (T = 64 key chunks, monotone in K: position >> shift, or quantile splitters of a key sample):
-//   S  vox_splitter_kernel   reflectance only: sort a 1024-key sample in one CTA -> 63 coarse + 511 fine splitters
-//   A  vox_scatter_kernel    per point: cell -> compact cell row q (claimed on first touch, atomicCAS on a dense map),
-//                            first[q] = min K, cnt[q][chunk(K)] += 1
-//   Q1 vox_cell_prefix_kernel  per cell: cnt -> inclusive prefix over chunks; histogram of fine bins of first[q]
-//   Q2 vox_bucket_kernel       per cell: bucket the cells by fine bin
-//   Q3 vox_rank_kernel         per cell: pillar id = bin base + rank inside the bucket; coors, cutoff, voxel_num
-//   C  vox_place_kernel      per point: window [prefix(chunk-1), prefix(chunk)) of its cell's sorted row; points
-//                            of different chunks never touch the same slots, equal-chunk points (a handful) settle
-//                            their order with a lock-free atomicMin insertion chain -> slot order of the reference
-//   D  vox_gather_kernel     voxels[m][s] = points[row[m][s]], zero padded; num_points
+// Kernels (64 key chunks per cell, monotone in K: geometric in the position, or geometric quantiles of a key sample):
+//   S  vox_init_kernel        workspace fill; reflectance order: one CTA sorts a 1024-key sample -> 63 coarse chunk
+//                             splitters + 1023 fine splitters
+//   A  vox_scatter_kernel     per point: cell -> compact cell row q (claimed on first touch, atomicCAS on a dense map,
+//                             looked up through L1 afterwards), ticket = cnt[q][chunk(K)]++
+//   Q  vox_cell_prefix_kernel per cell (warp): counts -> inclusive prefix over the chunks, saturation chunk
+//   C  vox_place_kernel       per point: window [prefix(chunk-1), prefix(chunk)) of its cell's row.  Untruncated
+//                             windows are filled in arrival (ticket) order, the truncated one by a lock-free
+//                             atomicMin insertion chain; the points of a cell's lowest chunk also set first[q] = min K
+//   R  vox_rank_kernel        cooperative launch, two grid barriers: bin the cells by first[q] | bucket | pillar id =
+//                             bucket base + rank inside the bucket; coors, pillar_map, cutoff, voxel_num
+//   D  vox_gather*_kernel     per pillar: sort the row, drop keys >= cutoff, voxels[m][s] = points[row[s]]
 // Everything but the 16 B/point read and the output write is L2-resident workspace traffic.
 #include <math_constants.h>
 
@@ -32,7 +33,9 @@ namespace {
 typedef unsigned long long u64;
 constexpr int VOX_THREADS = 256;
 constexpr int NCHUNK = 64;          // coarse key chunks per cell
-constexpr int NFINE = 1024;         // fine bins used to rank the cells' first keys
+constexpr int NFINE = 1024;         // sample intervals used to rank the cells' first keys
+constexpr int NSUB = 8;             // linear sub-bins per sample interval (64-bit keys)
+constexpr int NBIN = NFINE * NSUB;  // ranking bins
 constexpr int SAMPLE = 1024;        // keys sampled for the quantile splitters (one per sorting thread)
 
 template <typename K> struct KeyInf;
@@ -53,7 +56,7 @@ struct VoxParams {
 struct VoxBuf {
     int32_t *map;          // [cells]  cell -> q, -1 empty, -2 being claimed
     int32_t *counters;     // [0] nq
-    int32_t r_init;        // rows [0, r_init) are initialised up front
+    int32_t r_rows;        // cnt rows [0, r_rows) are zeroed up front, later rows by the claiming thread
     int32_t *base;         // [NFINE + 1] exclusive scan of hist (written by the bucket kernel)
     void *cutoff;          // key
     int32_t *cell_of_q;    // [Q]
@@ -193,24 +196,22 @@ vox_init_kernel(const float *__restrict__ points, int64_t n, int C, int wide, u6
 }
 
 // ---- A: per point ------------------------------------------------------------------------------------------
-template <typename K>
-__device__ __forceinline__ int claim_row(const VoxBuf &w, int32_t cell, int P)
+// Row of a cell.  A published row id never changes, so the first look goes through L1 (plain load: a stale line can
+// only still say "empty", which falls through to the coherent path); only the first touch of a cell claims a row.
+__device__ __forceinline__ int claim_row(const VoxBuf &w, int32_t cell)
 {
     int q = __ldcg(w.map + cell);
     while (q < 0) {
         if (q == -1) {
             int old = atomicCAS(w.map + cell, -1, -2);
             if (old == -1) {
-                // first touch: allocate a compact row; rows >= r_init were not initialised by vox_init_kernel
+                // first touch: allocate a compact row; counter rows >= r_rows were not zeroed by vox_init_kernel
                 q = atomicAdd(w.counters, 1);
                 w.cell_of_q[q] = cell;
-                if (q >= w.r_init) {
-                    ((K *)w.first)[q] = KeyInf<K>::value();
+                if (q >= w.r_rows) {
                     int4 *c4 = reinterpret_cast<int4 *>(w.cnt + (size_t)q * NCHUNK);
 #pragma unroll
                     for (int k = 0; k < NCHUNK / 4; ++k) c4[k] = make_int4(0, 0, 0, 0);
-                    K *row = (K *)w.rows + (size_t)q * P;
-                    for (int k = 0; k < P; ++k) row[k] = KeyInf<K>::value();
                     __threadfence();
                 }
                 atomicExch(w.map + cell, q);
@@ -224,72 +225,112 @@ __device__ __forceinline__ int claim_row(const VoxBuf &w, int32_t cell, int P)
     return q;
 }
 
+// Chunk of a 64-bit key = number of coarse splitters <= key.  The search runs on the splitters' high words (the
+// reflectance part); the low words only matter when a splitter shares the key's reflectance bits.
+struct CoarseTable {
+    uint32_t hi[NCHUNK], lo[NCHUNK];
+};
+__device__ __forceinline__ void load_coarse(CoarseTable &t, const u64 *coarse)
+{
+    if (threadIdx.x < NCHUNK) {
+        const u64 v = threadIdx.x < NCHUNK - 1 ? coarse[threadIdx.x] : ~0ull;
+        t.hi[threadIdx.x] = (uint32_t)(v >> 32);
+        t.lo[threadIdx.x] = (uint32_t)v;
+    }
+}
+__device__ __forceinline__ int coarse_chunk(const CoarseTable &t, uint32_t prim, uint32_t idx)
+{
+    int lo = 0, hi = NCHUNK - 1;          // upper bound over the 63 real splitters
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+        const int mid = (lo + hi) >> 1;
+        if (lo < hi) { if (t.hi[mid] <= prim) lo = mid + 1; else hi = mid; }
+    }
+    while (lo > 0 && t.hi[lo - 1] == prim && t.lo[lo - 1] > idx) --lo;     // equal reflectance bits: order by index
+    return lo;
+}
+
+constexpr int SC_IT = 4;      // points per thread and iteration: their dependent chains (map -> counter) are interleaved
+
 template <typename K>
 __global__ void __launch_bounds__(VOX_THREADS)
 vox_scatter_kernel(const float *__restrict__ points, int64_t n, const VoxParams prm, const int32_t *__restrict__ perm,
                    const VoxBuf w)
 {
     pdl_enter();
-    __shared__ u64 s_coarse[NCHUNK];
+    __shared__ CoarseTable s_ct;
     constexpr bool WIDE = sizeof(K) == 8;
     if (WIDE) {
-        if (threadIdx.x < NCHUNK - 1) s_coarse[threadIdx.x] = w.coarse[threadIdx.x];
+        load_coarse(s_ct, w.coarse);
         __syncthreads();
     }
-    const int64_t p = (int64_t)blockIdx.x * VOX_THREADS + threadIdx.x;
-    if (p >= n) return;
-    const int64_t idx = perm ? (int64_t)(uint32_t)perm[p] : p;
-    float x, y, z, refl = 0.f;
-    if (prm.vec4) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(points) + idx);
-        x = v.x; y = v.y; z = v.z; refl = v.w;
-    } else {
-        const float *pt = points + idx * prm.C;
-        x = __ldg(pt); y = __ldg(pt + 1); z = __ldg(pt + 2);
-        if (WIDE) refl = __ldg(pt + 3);
+    for (int64_t b0 = (int64_t)blockIdx.x * (VOX_THREADS * SC_IT); b0 < n; b0 += (int64_t)gridDim.x * (VOX_THREADS * SC_IT)) {
+        const int64_t p0 = b0 + threadIdx.x;
+        int32_t cell[SC_IT];
+        float refl[SC_IT];
+#pragma unroll
+        for (int k = 0; k < SC_IT; ++k) {
+            const int64_t p = p0 + k * VOX_THREADS;
+            cell[k] = -1;
+            refl[k] = 0.f;
+            if (p >= n) continue;
+            const int64_t idx = perm ? (int64_t)(uint32_t)perm[p] : p;
+            float x, y, z;
+            if (prm.vec4) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(points) + idx);
+                x = v.x; y = v.y; z = v.z; refl[k] = v.w;
+            } else {
+                const float *pt = points + idx * prm.C;
+                x = __ldg(pt); y = __ldg(pt + 1); z = __ldg(pt + 2);
+                if (WIDE) refl[k] = __ldg(pt + 3);
+            }
+            int cx, cy, cz;
+            // cell linearisation (z*gy + y)*gx + x = the (D,H,W) order of the BEV canvas
+            if (axis_cell(prm, 0, x, cx) && axis_cell(prm, 1, y, cy) && axis_cell(prm, 2, z, cz))
+                cell[k] = (cz * prm.g[1] + cy) * prm.g[0] + cx;
+        }
+        int q[SC_IT];
+#pragma unroll
+        for (int k = 0; k < SC_IT; ++k) q[k] = cell[k] >= 0 ? w.map[cell[k]] : -1;      // L1 look (see claim_row)
+        int t[SC_IT];
+#pragma unroll
+        for (int k = 0; k < SC_IT; ++k) {
+            const int64_t p = p0 + k * VOX_THREADS;
+            t[k] = 0;
+            if (cell[k] < 0) continue;
+            if (q[k] < 0) q[k] = claim_row(w, cell[k]);
+            int ch;
+            if (WIDE) {
+                const uint32_t prim = ~ordered_bits(refl[k]);
+                w.key_of_point[p] = prim;
+                ch = coarse_chunk(s_ct, prim, (uint32_t)p);
+            } else {
+                ch = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
+            }
+            t[k] = atomicAdd(w.cnt + (size_t)q[k] * NCHUNK + ch, 1);
+        }
+#pragma unroll
+        for (int k = 0; k < SC_IT; ++k) {
+            const int64_t p = p0 + k * VOX_THREADS;
+            if (p >= n) continue;
+            w.q_of_point[p] = cell[k] >= 0 ? q[k] : -1;
+            if (cell[k] >= 0) w.tick[p] = (uint8_t)(t[k] < 255 ? t[k] : 255);
+        }
     }
-    int cx, cy, cz;
-    if (!(axis_cell(prm, 0, x, cx) && axis_cell(prm, 1, y, cy) && axis_cell(prm, 2, z, cz))) {
-        w.q_of_point[p] = -1;
-        return;
-    }
-    // cell linearisation (z*gy + y)*gx + x = the (D,H,W) order of the BEV canvas
-    const int32_t cell = (cz * prm.g[1] + cy) * prm.g[0] + cx;
-    const int q = claim_row<K>(w, cell, prm.P);
-    K key;
-    int ch;
-    if (WIDE) {
-        const uint32_t prim = ~ordered_bits(refl);
-        w.key_of_point[p] = prim;
-        key = (K)(((u64)prim << 32) | (uint32_t)p);
-        ch = upper_bound_u64(s_coarse, NCHUNK - 1, (u64)key);
-    } else {
-        key = (K)(uint32_t)p;
-        ch = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
-    }
-    w.q_of_point[p] = q;
-    K *first = (K *)w.first + q;
-    if (key < __ldcg(first)) key_min(first, key);                // most points do not lower the minimum (L2 read, not .sys)
-    const int t = atomicAdd(w.cnt + (size_t)q * NCHUNK + ch, 1);
-    w.tick[p] = (uint8_t)(t < 255 ? t : 255);
 }
 
-// ---- Q1..Q3: per occupied cell --------------------------------------------------------------------------------
+// ---- Q1: per occupied cell, before the placement -----------------------------------------------------------------
 constexpr int Q1_THREADS = 1024;   // 32 cells per CTA, one warp each
 
-// Q1: one warp per cell: counts -> inclusive prefix over the 64 chunks (two chunks per lane, coalesced), fine bin
-// of the cell's first key; the bins are aggregated in shared memory before they reach the global histogram.
+// One warp per cell: counts -> inclusive prefix over the 64 chunks (two chunks per lane, coalesced), the saturation
+// chunk, first[q] = +inf, and +inf in the slots the placement fills by sorted insertion.
 template <typename K>
 __global__ void __launch_bounds__(Q1_THREADS) vox_cell_prefix_kernel(const VoxParams prm, const VoxBuf w)
 {
     pdl_enter();
-    __shared__ int s_hist[NFINE];
-    constexpr bool WIDE = sizeof(K) == 8;
     const int nq = w.counters[0];
-    if ((int)(blockIdx.x * (Q1_THREADS / 32)) >= nq) return;
-    for (int i = threadIdx.x; i < NFINE; i += Q1_THREADS) s_hist[i] = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31;
+    const int P = prm.P;
     for (int q = blockIdx.x * (Q1_THREADS / 32) + (threadIdx.x >> 5); q < nq; q += gridDim.x * (Q1_THREADS / 32)) {
         int2 *c2 = reinterpret_cast<int2 *>(w.cnt + (size_t)q * NCHUNK) + lane;
         int2 v = *c2;
@@ -305,120 +346,25 @@ __global__ void __launch_bounds__(Q1_THREADS) vox_cell_prefix_kernel(const VoxPa
         v.y += excl;
         *c2 = v;
         // first chunk at which the cell already holds max_points points: later chunks are dropped unseen
-        int sat = v.x >= prm.P ? 2 * lane : (v.y >= prm.P ? 2 * lane + 1 : NCHUNK);
+        int sat = v.x >= P ? 2 * lane : (v.y >= P ? 2 * lane + 1 : NCHUNK);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sat = min(sat, __shfl_xor_sync(0xFFFFFFFFu, sat, o));
+        K *row = (K *)w.rows + (size_t)q * P;
+        if (prm.ticket) {
+            // only a truncated window (more points than free slots) is filled by sorted insertion
+            if (sat < NCHUNK) {
+                const int src = sat > 0 ? (sat - 1) >> 1 : 0;
+                const int bx = __shfl_sync(0xFFFFFFFFu, v.x, src), by = __shfl_sync(0xFFFFFFFFu, v.y, src);
+                const int wbase = sat == 0 ? 0 : (((sat - 1) & 1) ? by : bx);
+                for (int s = wbase + lane; s < P; s += 32) row[s] = KeyInf<K>::value();
+            }
+        } else {
+            for (int s = lane; s < P; s += 32) row[s] = KeyInf<K>::value();
+        }
         if (lane == 0) {
             w.sat_of_q[q] = (uint8_t)sat;
-            const K f = ((const K *)w.first)[q];
-            int bin;
-            if (WIDE) bin = upper_bound_u64(w.fine, NFINE - 1, (u64)f);
-            else bin = geo_bin<F_OCT, F_SUB>((uint32_t)f, prm.bits);
-            w.bin_of_q[q] = bin;
-            atomicAdd(s_hist + bin, 1);
+            ((K *)w.first)[q] = KeyInf<K>::value();
         }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NFINE; i += Q1_THREADS)
-        if (s_hist[i]) atomicAdd(w.hist + i, s_hist[i]);
-}
-
-// exclusive scan of the NFINE-bin histogram into shared memory
-__device__ __forceinline__ void scan_hist(const int32_t *__restrict__ hist, int *s_base /* [NFINE + 1] */)
-{
-    __shared__ int s_warp[VOX_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int PER = NFINE / VOX_THREADS;
-    int v[PER], sum = 0;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) { v[k] = hist[tid * PER + k]; sum += v[k]; }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    int base = incl - sum;
-    for (int k = 0; k < warp; ++k) base += s_warp[k];
-#pragma unroll
-    for (int k = 0; k < PER; ++k) { s_base[tid * PER + k] = base; base += v[k]; }
-    if (tid == VOX_THREADS - 1) s_base[NFINE] = base;
-    __syncthreads();
-}
-
-// Q2: one thread per cell: bucket the cells by fine bin (one global atomic per CTA and bin)
-template <typename K>
-__global__ void __launch_bounds__(VOX_THREADS) vox_bucket_kernel(const VoxBuf w)
-{
-    pdl_enter();
-    __shared__ int s_base[NFINE + 1];
-    __shared__ int s_cnt[NFINE], s_off[NFINE];
-    const int nq = w.counters[0];
-    if ((int)(blockIdx.x * VOX_THREADS) >= nq) return;
-    scan_hist(w.hist, s_base);
-    if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i <= NFINE; i += VOX_THREADS) w.base[i] = s_base[i];   // for the rank kernel
-    for (int q0 = blockIdx.x * VOX_THREADS; q0 < nq; q0 += gridDim.x * VOX_THREADS) {   // CTA-uniform trip count
-        for (int i = threadIdx.x; i < NFINE; i += VOX_THREADS) s_cnt[i] = 0;
-        __syncthreads();
-        const int q = q0 + threadIdx.x;
-        int bin = 0, local = 0;
-        if (q < nq) {
-            bin = w.bin_of_q[q];
-            local = atomicAdd(s_cnt + bin, 1);               // position inside this CTA's share of the bucket
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < NFINE; i += VOX_THREADS)
-            if (s_cnt[i]) s_off[i] = atomicAdd(w.fill + i, s_cnt[i]);
-        __syncthreads();
-        if (q < nq) {
-            const int slot = s_base[bin] + s_off[bin] + local;
-            w.list[slot] = q;
-            ((K *)w.lkey)[slot] = ((const K *)w.first)[q];   // keys in bucket order: contiguous reads when ranking
-        }
-        __syncthreads();
-    }
-}
-
-// Q3: one warp per bucket slot: pillar id = bucket base + number of smaller first keys in the bucket (the lanes
-// stride over the bucket's contiguous keys), then coors / cutoff / voxel_num.
-template <typename K>
-__global__ void __launch_bounds__(VOX_THREADS)
-vox_rank_kernel(const VoxParams prm, const VoxBuf w, int32_t *__restrict__ coors, int32_t *__restrict__ voxel_num,
-                int32_t *__restrict__ pillar_map)
-{
-    pdl_enter();
-    const int nq = w.counters[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *voxel_num = nq < prm.max_voxels ? nq : prm.max_voxels;
-    const int lane = threadIdx.x & 31;
-    const K *lkey = (const K *)w.lkey;
-    for (int t = blockIdx.x * (VOX_THREADS / 32) + (threadIdx.x >> 5); t < nq; t += gridDim.x * (VOX_THREADS / 32)) {
-    const int q = w.list[t];
-    const int bin = w.bin_of_q[q];
-    const K f = lkey[t];
-    const int b0 = w.base[bin], b1 = w.base[bin + 1];
-    int cnt = 0;
-    for (int j = b0 + lane; j < b1; j += 32) cnt += (lkey[j] < f) ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-    if (lane != 0) continue;
-    const int rank = b0 + cnt;
-    const K f0 = f;
-    if (rank < prm.max_voxels) {
-        w.pid_of_q[q] = rank;
-        w.q_of_pid[rank] = q;
-        const int c = w.cell_of_q[q];
-        const int cx = c % prm.g[0], tt = c / prm.g[0];
-        coors[rank * 3 + 0] = cx;
-        coors[rank * 3 + 1] = tt % prm.g[1];
-        coors[rank * 3 + 2] = tt / prm.g[1];
-        if (pillar_map) pillar_map[c] = rank;
-    } else {
-        w.pid_of_q[q] = -1;
-        if (rank == prm.max_voxels) *(K *)w.cutoff = f0;    // the reference breaks here (:223, :291)
-    }
     }
 }
 
@@ -428,20 +374,20 @@ constexpr int PLACE_TABLE = 40 * 1024;      // cells whose saturation chunk is c
 
 // Persistent CTAs: the per-cell saturation chunk (1 byte per cell) is staged in shared memory once per CTA, so the
 // majority of the points -- those of already full pillars -- are rejected without any random global access.
+// The points of a cell's lowest occupied chunk (window base 0) also settle the cell's smallest key, first[q].
 template <typename K>
 __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, const VoxParams prm, const VoxBuf w)
 {
     pdl_enter();
-    __shared__ u64 s_coarse[NCHUNK];
+    __shared__ CoarseTable s_ct;
     __shared__ __align__(16) uint8_t s_sat[PLACE_TABLE];
     constexpr bool WIDE = sizeof(K) == 8;
-    if (WIDE && threadIdx.x < NCHUNK - 1) s_coarse[threadIdx.x] = w.coarse[threadIdx.x];
+    if (WIDE) load_coarse(s_ct, w.coarse);
     const int nq = w.counters[0];
     const int ntab = nq < PLACE_TABLE ? nq : PLACE_TABLE;
     for (int i = threadIdx.x; i * 16 < ntab; i += PLACE_THREADS)
         reinterpret_cast<uint4 *>(s_sat)[i] = reinterpret_cast<const uint4 *>(w.sat_of_q)[i];
     __syncthreads();
-    const K cutoff = *(const K *)w.cutoff;
     const int P = prm.P;
     // Four points per thread and iteration: their loads, and later their insertion chains, are issued back to back
     // (an in-order warp stalls at the first use of a result, so one point at a time would serialise every L2 round
@@ -471,14 +417,13 @@ __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, con
             if (!act[k]) continue;
             if (WIDE) {
                 key[k] = (K)(((u64)prim[k] << 32) | (uint32_t)p);
-                ch[k] = upper_bound_u64(s_coarse, NCHUNK - 1, (u64)key[k]);
+                ch[k] = coarse_chunk(s_ct, prim[k], (uint32_t)p);
             } else {
                 key[k] = (K)(uint32_t)p;
                 ch[k] = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
             }
             const int sat = q[k] < PLACE_TABLE ? (int)s_sat[q[k]] : (int)w.sat_of_q[q[k]];
-            // full before this chunk (:303), or at / after the break
-            if (ch[k] > sat || key[k] >= cutoff) { act[k] = false; continue; }
+            if (ch[k] > sat) { act[k] = false; continue; }      // the pillar is full before this chunk (:303)
             const int32_t *incl = w.cnt + (size_t)q[k] * NCHUNK;
             base[k] = ch[k] ? incl[ch[k] - 1] : 0;
             end[k] = incl[ch[k]];
@@ -496,9 +441,11 @@ __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, con
             K *row = (K *)w.rows + (size_t)q[k] * P;
             if (end[k] - base[k] == 1) {                     // alone in its window: the slot is known
                 row[base[k]] = key[k];
+                if (base[k] == 0) ((K *)w.first)[q[k]] = key[k];      // ... and so is the cell's smallest key
                 act[k] = false;
                 continue;
             }
+            if (base[k] == 0) key_min((K *)w.first + q[k], key[k]);  // lowest occupied chunk of the cell
             if (prm.ticket && end[k] <= P) {                 // the whole window is kept: arrival order now, the
                 row[base[k] + tk[k]] = key[k];               // gather kernel sorts the row
                 act[k] = false;
@@ -527,7 +474,165 @@ __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, con
     }
 }
 
+// ---- R: rank the cells by their smallest key -----------------------------------------------------------------------
+// One cooperative launch, two grid barriers:
+//   1  fine bin of first[q]; arrival index inside the bin (global histogram)
+//   2  exclusive scan of the histogram (every CTA, shared memory); cells bucketed by bin, keys in bucket order
+//   3  pillar id = bucket base + number of smaller keys in the bucket; coors, pillar_map, cutoff, voxel_num
+constexpr int RANK_THREADS = 1024;
+
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*((volatile unsigned *)bar) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <typename K>
+__global__ void __launch_bounds__(RANK_THREADS)
+vox_rank_kernel(const VoxParams prm, const VoxBuf w, int32_t *__restrict__ coors, int32_t *__restrict__ voxel_num,
+                int32_t *__restrict__ pillar_map, int64_t n_points)
+{
+    constexpr bool WIDE = sizeof(K) == 8;
+    extern __shared__ __align__(16) unsigned char rk_smem[];
+    int *s_base = reinterpret_cast<int *>(rk_smem);                          // [NBIN + 1]
+    u64 *s_fine = reinterpret_cast<u64 *>(rk_smem + (NBIN + 4) * sizeof(int));   // [NFINE], later the staged keys
+    __shared__ int s_warp[RANK_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_enter();
+    const int nq = w.counters[0];
+    unsigned *bar = (unsigned *)(w.counters + 8);
+    if (WIDE) {
+        for (int i = tid; i < NFINE - 1; i += RANK_THREADS) s_fine[i] = w.fine[i];
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        *voxel_num = nq < prm.max_voxels ? nq : prm.max_voxels;
+        *(K *)w.cutoff = KeyInf<K>::value();
+    }
+    // ---- 1
+    // intervals [0, istar) get nsub sub-bins each, the others one bin: istar * nsub + (NFINE - istar) <= NBIN
+    int istar = (int)(((int64_t)NFINE * 3 * nq) / (n_points > 0 ? n_points : 1)) + 8;
+    istar = istar > NFINE - 1 ? NFINE - 1 : istar;
+    const int nsub = (NBIN - NFINE) / istar;
+    for (int q = blockIdx.x * RANK_THREADS + tid; q < nq; q += gridDim.x * RANK_THREADS) {
+        const K f = ((const K *)w.first)[q];
+        int bin;
+        if (WIDE) {
+            // Sample interval of the key, then a linear position inside the interval (on the reflectance bits).  A
+            // cell with m points has its smallest key near the 1/m quantile, so the smallest keys crowd into the
+            // first ~ nq / n of the key space: the intervals below `istar` share most of the bins.
+            const int i = upper_bound_u64(s_fine, NFINE - 1, (u64)f);
+            if (i >= istar) {
+                bin = istar * nsub + (i - istar);
+            } else {
+                u64 lo, hi = s_fine[i];
+                if (i > 0) lo = s_fine[i - 1];
+                else { const u64 wd = s_fine[1] - s_fine[0]; lo = s_fine[0] > wd ? s_fine[0] - wd : 0ull; }
+                int sub = 0;
+                if ((u64)f > lo) {
+                    const u64 num = (((u64)f - lo) >> 32) * (u64)nsub, den = ((hi - lo) >> 32) + 1ull;
+                    sub = (int)(num / den);
+                }
+                bin = i * nsub + (sub < nsub - 1 ? sub : nsub - 1);
+            }
+        } else {
+            bin = geo_bin<F_OCT, F_SUB>((uint32_t)f, prm.bits);
+        }
+        w.bin_of_q[q] = bin;
+        w.pid_of_q[q] = atomicAdd(w.hist + bin, 1);            // arrival index inside the bin, until step 3
+    }
+    grid_barrier(bar, gridDim.x);
+    // ---- 2
+    {
+        constexpr int PER = NBIN / RANK_THREADS;
+        int v[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { v[k] = __ldcg(w.hist + tid * PER + k); sum += v[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int base = incl - sum;
+        for (int k = 0; k < warp; ++k) base += s_warp[k];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { s_base[tid * PER + k] = base; base += v[k]; }
+        if (tid == RANK_THREADS - 1) s_base[NBIN] = base;
+        __syncthreads();
+    }
+    for (int q = blockIdx.x * RANK_THREADS + tid; q < nq; q += gridDim.x * RANK_THREADS) {
+        const int slot = s_base[w.bin_of_q[q]] + w.pid_of_q[q];
+        w.list[slot] = q;
+        ((K *)w.lkey)[slot] = ((const K *)w.first)[q];         // keys in bucket order: contiguous reads when ranking
+    }
+    grid_barrier(bar, 2 * gridDim.x);
+    // ---- 3: eight lanes per bucket slot.  The cells' smallest keys crowd into the lowest bins (a cell with n points
+    // has its minimum near the 1/n quantile), so buckets are long and shared by many slots: a CTA takes 128
+    // consecutive slots per step and stages the key range of their buckets in shared memory.
+    constexpr int GL = 8, SL = RANK_THREADS / GL, CH = 1024;
+    K *s_keys = reinterpret_cast<K *>(s_fine);        // the splitters are no longer needed
+    __shared__ int s_rng[2];
+    const K *lkey = (const K *)w.lkey;
+    const int sub = lane & (GL - 1);
+    const unsigned gmask = 0xFFu << (lane & ~(GL - 1));
+    for (int slot0 = blockIdx.x * SL; slot0 < nq; slot0 += gridDim.x * SL) {
+        const int t = slot0 + tid / GL;
+        const bool valid = t < nq;
+        int q = 0, b0 = 0, b1 = 0;
+        K f = 0;
+        if (valid) {
+            q = __ldcg(w.list + t);
+            f = __ldcg(lkey + t);
+            const int bin = __ldcg(w.bin_of_q + q);
+            b0 = s_base[bin];
+            b1 = s_base[bin + 1];
+        }
+        const int t_last = min(slot0 + SL, nq) - 1;
+        if (tid == 0) s_rng[0] = b0;                                  // slots are in bucket order
+        if (t == t_last && sub == 0) s_rng[1] = b1;
+        __syncthreads();
+        const int r0 = s_rng[0], r1 = s_rng[1];
+        int cnt = 0;
+        for (int c0 = r0; c0 < r1; c0 += CH) {
+            const int cn = min(CH, r1 - c0);
+            for (int i = tid; i < cn; i += RANK_THREADS) s_keys[i] = __ldcg(lkey + c0 + i);
+            __syncthreads();
+            const int j0 = max(b0, c0), j1 = min(b1, c0 + cn);
+            for (int j = j0 + sub; j < j1; j += GL) cnt += (s_keys[j - c0] < f) ? 1 : 0;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int o = GL / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
+        if (!valid || sub != 0) continue;
+        const int rank = b0 + cnt;
+        if (rank < prm.max_voxels) {
+            const int c = w.cell_of_q[q];
+            w.pid_of_q[q] = rank;
+            w.q_of_pid[rank] = q;
+            const int cx = c % prm.g[0], tt = c / prm.g[0];
+            coors[rank * 3 + 0] = cx;
+            coors[rank * 3 + 1] = tt % prm.g[1];
+            coors[rank * 3 + 2] = tt / prm.g[1];
+            if (pillar_map) pillar_map[c] = rank;
+        } else {
+            w.pid_of_q[q] = -1;
+            if (rank == prm.max_voxels) *(K *)w.cutoff = f;    // the reference breaks here (:223, :291)
+        }
+    }
+}
+
 // ---- D: gather ---------------------------------------------------------------------------------------------------
+// Keys at or after the cutoff (the first key of the pillar the reference breaks on) are dropped here: they are the
+// largest keys of their rows, so the slots before them are unaffected.
 template <typename K, bool VEC4>
 __global__ void __launch_bounds__(VOX_THREADS)
 vox_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ perm, const VoxBuf w,
@@ -540,10 +645,11 @@ vox_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ 
     const int64_t m = t / P;
     const int s = (int)(t - m * P);
     if (m >= *voxel_num) return;
+    const K cutoff = *(const K *)w.cutoff;
     const K *row = (const K *)w.rows + (size_t)w.q_of_pid[m] * P;
     const K key = row[s];
-    const bool valid = key != KeyInf<K>::value();
-    if (valid && (s == P - 1 || row[s + 1] == KeyInf<K>::value())) num_points[m] = s + 1;
+    const bool valid = key < cutoff;                         // +inf (empty slot) is never below the cutoff
+    if (valid && (s == P - 1 || !(row[s + 1] < cutoff))) num_points[m] = s + 1;
     int64_t idx = 0;
     if (valid) {
         const uint32_t pos = (uint32_t)key;                  // low word = position / original index
@@ -579,10 +685,16 @@ vox_gather_sorted_kernel(const float *__restrict__ points, const int32_t *__rest
     pdl_enter();
     const int lane = threadIdx.x & 31;
     const int nvox = *voxel_num;
+    const K cutoff = *(const K *)w.cutoff;
     for (int m = blockIdx.x * (VOX_THREADS / 32) + (threadIdx.x >> 5); m < nvox; m += gridDim.x * (VOX_THREADS / 32)) {
-        const K *row = (const K *)w.rows + (size_t)w.q_of_pid[m] * P;
-        K k0 = lane < P ? row[lane] : KeyInf<K>::value();
-        K k1 = (TWO && lane + 32 < P) ? row[lane + 32] : KeyInf<K>::value();
+        const int q = w.q_of_pid[m];
+        const K *row = (const K *)w.rows + (size_t)q * P;
+        const int total = w.cnt[(size_t)q * NCHUNK + NCHUNK - 1];      // inclusive prefix of the last chunk
+        const int nk = total < P ? total : P;                          // slots [0, nk) were written by the placement
+        K k0 = lane < nk ? row[lane] : KeyInf<K>::value();
+        K k1 = (TWO && lane + 32 < nk) ? row[lane + 32] : KeyInf<K>::value();
+        if (!(k0 < cutoff)) k0 = KeyInf<K>::value();
+        if (!(k1 < cutoff)) k1 = KeyInf<K>::value();
         // bitonic sort of 32 (or 64) keys, element index e = r * 32 + lane
 #pragma unroll
         for (int size = 2; size <= (TWO ? 64 : 32); size <<= 1) {
@@ -660,17 +772,17 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
     const int64_t cells = (int64_t)c->grid[0] * c->grid[1] * c->grid[2];
     r.Q = n1 < cells ? n1 : cells;
     const size_t ksz = wide ? 8 : 4;
-    // rows initialised up front: a bit more than the pillar cap; beyond that the claiming thread initialises
-    int64_t r_init = (int64_t)c->max_voxels + c->max_voxels / 4 + 1024;
-    if (r_init > r.Q) r_init = r.Q;
-    r.b.r_init = (int32_t)r_init;
+    // counter rows zeroed up front: a bit more than the pillar cap; beyond that the claiming thread zeroes its row
+    int64_t r_rows = (int64_t)c->max_voxels + c->max_voxels / 4 + 1024;
+    if (r_rows > r.Q) r_rows = r.Q;
+    r.b.r_rows = (int32_t)r_rows;
     Arena a(ws, (size_t)-1);
     r.b.map = a.take<int32_t>((size_t)cells);
     r.b.cutoff = a.take<u64>(8);
     const size_t ff0_bytes = a.off;                          // map + cutoff, contiguous, 0xFF
     r.b.counters = a.take<int32_t>(64);
-    r.b.hist = a.take<int32_t>(NFINE);
-    r.b.fill = a.take<int32_t>(NFINE);
+    r.b.hist = a.take<int32_t>(NBIN);
+    r.b.fill = a.take<int32_t>(16);
     const size_t z0_off = (size_t)((char *)r.b.counters - (char *)ws), z0_bytes = a.off - z0_off;
     r.b.base = a.take<int32_t>(NFINE + 1);
     r.b.cell_of_q = a.take<int32_t>((size_t)r.Q);
@@ -691,11 +803,11 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
     *total = align_up(a.off);
     // every array starts 256-byte aligned, so rounding the fills up to 16 bytes stays inside the padding
     r.ia.ff_ptr[0] = (int4 *)r.b.map;    r.ia.ff_n[0] = units16(ff0_bytes);
-    r.ia.ff_ptr[1] = (int4 *)r.b.first;  r.ia.ff_n[1] = units16((size_t)r_init * ksz);
-    r.ia.ff_ptr[2] = (int4 *)r.b.rows;   r.ia.ff_n[2] = units16((size_t)r_init * c->max_points * ksz);
+    r.ia.ff_ptr[1] = nullptr;            r.ia.ff_n[1] = 0;
+    r.ia.ff_ptr[2] = nullptr;            r.ia.ff_n[2] = 0;
     r.ia.ff_ptr[3] = nullptr;            r.ia.ff_n[3] = 0;      // optional pillar_map, set by the caller
     r.ia.z_ptr[0] = (int4 *)((char *)ws + z0_off);  r.ia.z_n[0] = units16(z0_bytes);
-    r.ia.z_ptr[1] = (int4 *)r.b.cnt;     r.ia.z_n[1] = units16((size_t)r_init * NCHUNK * 4);
+    r.ia.z_ptr[1] = (int4 *)r.b.cnt;     r.ia.z_n[1] = units16((size_t)r_rows * NCHUNK * 4);
     return r;
 }
 
@@ -705,8 +817,6 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
 {
     const VoxBuf &w = cv.b;
     constexpr bool WIDE = sizeof(K) == 8;
-    const unsigned nb = (unsigned)ceil_div(n, VOX_THREADS);
-    const unsigned qb = (unsigned)ceil_div(cv.Q, VOX_THREADS);
     int64_t fill_units = 0;
     for (int r = 0; r < 4; ++r) fill_units += cv.ia.ff_n[r];
     for (int r = 0; r < 2; ++r) fill_units += cv.ia.z_n[r];
@@ -714,18 +824,51 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
     init_blocks = init_blocks < 1 ? 1 : (init_blocks > 148 * 2 ? 148 * 2 : init_blocks);
     launch_pdl(vox_init_kernel, dim3(init_blocks + (WIDE ? 1 : 0)), dim3(1024), 0, st, points, n, prm.C, WIDE ? 1 : 0, w.coarse, w.fine, cv.ia);
     if (int rc = check_launch("vox_init_kernel")) return rc;
-    launch_pdl(vox_scatter_kernel<K>, dim3(nb), dim3(VOX_THREADS), 0, st, points, n, prm, perm, w);
+    // persistent grid: exactly the CTAs that are resident at once (no partial last wave)
+    static int sc_resident = 0;
+    if (!sc_resident) {
+        int per_sm = 0, dev = 0, sms = 0;
+        PP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vox_scatter_kernel<K>, VOX_THREADS, 0));
+        PP_CUDA_TRY(cudaGetDevice(&dev));
+        PP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        sc_resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+    }
+    const int64_t sc_blocks = ceil_div(n, VOX_THREADS * SC_IT);
+    launch_pdl(vox_scatter_kernel<K>, dim3((unsigned)(sc_blocks < sc_resident ? sc_blocks : sc_resident)), dim3(VOX_THREADS), 0, st,
+               points, n, prm, perm, w);
     if (int rc = check_launch("vox_scatter_kernel")) return rc;
     const unsigned cap = 148 * 8;    // persistent-style grids: the cell count is only known on the device
     auto capped = [&](int64_t blocks) { return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap); };
     launch_pdl(vox_cell_prefix_kernel<K>, dim3(capped(ceil_div(cv.Q, Q1_THREADS / 32)) / 4 + 1), dim3(Q1_THREADS), 0, st, prm, w);
     if (int rc = check_launch("vox_cell_prefix_kernel")) return rc;
-    launch_pdl(vox_bucket_kernel<K>, dim3(capped(qb)), dim3(VOX_THREADS), 0, st, w);
-    if (int rc = check_launch("vox_bucket_kernel")) return rc;
-    launch_pdl(vox_rank_kernel<K>, dim3(capped(ceil_div(cv.Q, VOX_THREADS / 32))), dim3(VOX_THREADS), 0, st, prm, w, coors, voxel_num, pillar_map);
-    if (int rc = check_launch("vox_rank_kernel")) return rc;
     launch_pdl(vox_place_kernel<K>, dim3((unsigned)(ceil_div(n, PLACE_THREADS * 4) < 148 * 4 ? ceil_div(n, PLACE_THREADS * 4) : 148 * 4)), dim3(PLACE_THREADS), 0, st, n, prm, w);
     if (int rc = check_launch("vox_place_kernel")) return rc;
+    {
+        // cooperative: the CTAs meet at two grid barriers, so they must all be resident
+        int64_t rb = ceil_div(cv.Q, RANK_THREADS);
+        rb = rb < 1 ? 1 : (rb > 148 ? 148 : rb);
+        const size_t rk_smem = (NBIN + 4) * sizeof(int) + NFINE * sizeof(u64);
+        static bool rk_attr = false;
+        if (!rk_attr) {
+            PP_CUDA_TRY(cudaFuncSetAttribute(vox_rank_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rk_smem));
+            rk_attr = true;
+        }
+        void *args[] = {(void *)&prm, (void *)&w, (void *)&coors, (void *)&voxel_num, (void *)&pillar_map, (void *)&n};
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)rb);
+        cfg.blockDim = dim3(RANK_THREADS);
+        cfg.dynamicSmemBytes = rk_smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
+        PP_CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)vox_rank_kernel<K>, args));
+        if (int rc = check_launch("vox_rank_kernel")) return rc;
+    }
     const bool vec4 = prm.vec4 && ((uintptr_t)voxels % 16 == 0);
     if (prm.ticket) {
         const unsigned gs = (unsigned)(ceil_div(max_rows, VOX_THREADS / 32) < 148 * 8 ? ceil_div(max_rows, VOX_THREADS / 32) : 148 * 8);
