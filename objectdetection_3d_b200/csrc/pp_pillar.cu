@@ -165,57 +165,118 @@ pfn_kernel(const PillarIn a, const float *__restrict__ W, const float *__restric
     }
 }
 
-// Fast path of the fused single-layer PillarFeatureNet (Cin <= 12, U <= 64): the two weight rows a lane
-// owns live in registers for the whole grid-stride loop, the decorated row is read back as broadcast
-// 128-bit shared loads.  Dot products use FMA (T1 against the reference; the decoration stays bit-exact).
+// Fast path of the fused single-layer PillarFeatureNet (Cin <= 12, U <= 64): the two weight rows a lane owns live
+// in registers for the whole grid-stride loop, the decorated row is read back as broadcast 128-bit shared loads.
+// Dot products use packed FMAs (fma.rn.f32x2, two features per instruction; T1 against the reference's sgemm, the
+// decoration stays bit-exact).
 constexpr int PFN_LDI = 12;
+
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long *>(&c)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+
+// P <= 32: lane = slot while decorating (the pillar's points never leave registers until the decorated row is
+// staged for the broadcast reads), lane = channel pair while multiplying.  The mean is a shuffle tree here (T1; the
+// bit-exact sequential form is decorate_row, used by pp_decorate and the generic layer kernel).
 template <int CIN>
-__global__ void __launch_bounds__(PIL_THREADS)
+__global__ void __launch_bounds__(PIL_THREADS, 10)
 pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const float *__restrict__ scale,
                        const float *__restrict__ shift, int U, float *__restrict__ out)
 {
     pdl_enter();
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int P = a.P;
+    const int P = a.P, C = a.C;
     constexpr int Cin = CIN;
-    float *row = smem + warp * P * PFN_LDI;
-    float w0[PFN_LDI], w1[PFN_LDI];
+    constexpr int NP = (CIN + 1) / 2;          // feature pairs (the row is zero padded to PFN_LDI)
+    float *row = smem + warp * 32 * PFN_LDI;
+    float2 w0[NP], w1[NP];
     const int u0 = lane, u1 = lane + 32;
 #pragma unroll
-    for (int k = 0; k < PFN_LDI; ++k) {
-        w0[k] = (u0 < U && k < Cin) ? W[u0 * Cin + k] : 0.f;
-        w1[k] = (u1 < U && k < Cin) ? W[u1 * Cin + k] : 0.f;
+    for (int k = 0; k < NP; ++k) {
+        w0[k].x = (u0 < U && 2 * k < Cin) ? W[u0 * Cin + 2 * k] : 0.f;
+        w0[k].y = (u0 < U && 2 * k + 1 < Cin) ? W[u0 * Cin + 2 * k + 1] : 0.f;
+        w1[k].x = (u1 < U && 2 * k < Cin) ? W[u1 * Cin + 2 * k] : 0.f;
+        w1[k].y = (u1 < U && 2 * k + 1 < Cin) ? W[u1 * Cin + 2 * k + 1] : 0.f;
     }
     const float sc0 = u0 < U ? scale[u0] : 0.f, sh0 = u0 < U ? shift[u0] : 0.f;
     const float sc1 = u1 < U ? scale[u1] : 0.f, sh1 = u1 < U ? shift[u1] : 0.f;
     int64_t M = a.M;
     if (a.m_dev) { int64_t md = *a.m_dev; M = md < M ? md : M; }
     const int out_w = U + 1;
+    const bool vec4 = (C == 4) && ((reinterpret_cast<uintptr_t>(a.voxels) & 15) == 0);
     for (int64_t m = (int64_t)blockIdx.x * PIL_WARPS + warp; m < M; m += (int64_t)gridDim.x * PIL_WARPS) {
         const int n = load_num(a, m);
-        decorate_row(a, m, n, row, PFN_LDI, lane);
+        // ---- decorate: lane = slot
+        float f[PFN_LDI];
+#pragma unroll
+        for (int k = 0; k < PFN_LDI; ++k) f[k] = 0.f;
+        if (lane < P) {
+            const float *v = a.voxels + (m * P + lane) * C;
+            if (vec4) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(v));
+                f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < PFN_LDI - 5; ++k)
+                    if (k < C) f[k] = __ldg(v + k);
+            }
+        }
+        float sx = f[0], sy = f[1], sz = f[2];                  // zero padded slots add nothing (:493-494)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sx += __shfl_xor_sync(0xFFFFFFFFu, sx, o);
+            sy += __shfl_xor_sync(0xFFFFFFFFu, sy, o);
+            sz += __shfl_xor_sync(0xFFFFFFFFu, sz, o);
+        }
+        const float nf = (float)n;
+        const float mx_ = __fdiv_rn(sx, nf), my_ = __fdiv_rn(sy, nf), mz_ = __fdiv_rn(sz, nf);
+        int cx, cy;
+        load_xy(a, m, cx, cy);
+        const float pcx = __fadd_rn(__fmul_rn((float)cx, a.vx), a.x_off);   // :500-503
+        const float pcy = __fadd_rn(__fmul_rn((float)cy, a.vy), a.y_off);   // :505-508
+        const float x = f[0], y = f[1], z = f[2];
+#pragma unroll
+        for (int k = 0; k < PFN_LDI - 5; ++k)
+            if (k == C) {                                        // C is 3..7 here (C + 5 == CIN)
+                f[k + 0] = __fsub_rn(x, mx_);                    // :496
+                f[k + 1] = __fsub_rn(y, my_);
+                f[k + 2] = __fsub_rn(z, mz_);
+                f[k + 3] = __fsub_rn(x, pcx);
+                f[k + 4] = __fsub_rn(y, pcy);
+            }
+        // slots >= n are never read below (p_end), so the padding mask (:518-521) needs no multiply
+        float4 *r4 = reinterpret_cast<float4 *>(row + lane * PFN_LDI);
+        r4[0] = make_float4(f[0], f[1], f[2], f[3]);
+        r4[1] = make_float4(f[4], f[5], f[6], f[7]);
+        r4[2] = make_float4(f[8], f[9], f[10], f[11]);
         __syncwarp();
+        // ---- multiply: lane = channels (lane, lane + 32)
         const int p_end = n < P ? n : P;
-        // zero-padded slots take part in the max (:403-410): they contribute relu(shift)
-        float mx0 = (p_end < P) ? fmaxf(sh0, 0.f) : -CUDART_INF_F;
-        float mx1 = (p_end < P) ? fmaxf(sh1, 0.f) : -CUDART_INF_F;
+        // zero-padded slots take part in the max (:403-410): they contribute relu(shift).  relu(y) >= 0, so starting
+        // the running max at 0 (or relu(shift)) makes the explicit relu redundant.
+        float mx0 = (p_end < P) ? fmaxf(sh0, 0.f) : 0.f;
+        float mx1 = (p_end < P) ? fmaxf(sh1, 0.f) : 0.f;
+#pragma unroll 2
         for (int p = 0; p < p_end; ++p) {
             const float4 *f4 = reinterpret_cast<const float4 *>(row + p * PFN_LDI);
             const float4 fa = f4[0], fb = f4[1], fc = f4[2];
-            const float f[PFN_LDI] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w, fc.x, fc.y, fc.z, fc.w};
-            float acc0 = 0.f, acc1 = 0.f;
+            const float2 g[6] = {make_float2(fa.x, fa.y), make_float2(fa.z, fa.w), make_float2(fb.x, fb.y),
+                                 make_float2(fb.z, fb.w), make_float2(fc.x, fc.y), make_float2(fc.z, fc.w)};
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < PFN_LDI; ++k) {
-                if (k < Cin) {      // fused multiply-add: within T1 of the reference's sgemm, 2x fewer FP32 issues
-                    acc0 = __fmaf_rn(f[k], w0[k], acc0);
-                    acc1 = __fmaf_rn(f[k], w1[k], acc1);
-                }
+            for (int k = 0; k < NP; ++k) {
+                a0 = ffma2(g[k], w0[k], a0);
+                a1 = ffma2(g[k], w1[k], a1);
             }
-            float y0 = __fmaf_rn(acc0, sc0, sh0);
-            float y1 = __fmaf_rn(acc1, sc1, sh1);
-            mx0 = fmaxf(mx0, y0 > 0.f ? y0 : 0.f);
-            mx1 = fmaxf(mx1, y1 > 0.f ? y1 : 0.f);
+            mx0 = fmaxf(mx0, __fmaf_rn(a0.x + a0.y, sc0, sh0));
+            mx1 = fmaxf(mx1, __fmaf_rn(a1.x + a1.y, sc1, sh1));
         }
         float *o = out + m * out_w;
         if (u0 < U) o[u0] = mx0;
@@ -297,6 +358,47 @@ scatter_canvas_kernel(const float *__restrict__ feat, const int32_t *__restrict_
     }
 }
 
+// Canvas tile of 256 float4 columns (1024 consecutive cells) x a quarter of the channels per CTA: a thread owns one
+// column, so the pillar ids stay in registers and a channel step is 4 predicated loads + one 128-bit store; a CTA
+// writes 4 KB contiguous per channel row.  Columns never straddle planes (HW % 4 == 0).
+constexpr int CV_THREADS = 256;
+constexpr int CV_CGROUPS = 4;      // channel groups (blockIdx.y): channel c belongs to group c % CV_CGROUPS
+
+// PDL: the zeros do not depend on anything the predecessors on the stream compute, so they are written BEFORE
+// griddepcontrol.wait, i.e. while the (FP32-bound) PFN kernel is still running; after the wait only the columns that
+// hold a pillar (a few percent) are overwritten with features.
+__global__ void __launch_bounds__(CV_THREADS, 6)
+scatter_canvas_wave_kernel(const float *__restrict__ feat, const int32_t *__restrict__ map, int C, int D, int64_t HW,
+                           int64_t total_cols, float *__restrict__ canvas)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int64_t col = (int64_t)blockIdx.x * CV_THREADS + threadIdx.x;
+    const int cq = blockIdx.y;
+    const int64_t hw4 = HW >> 2;
+    const int64_t plane = col / hw4, cell = (col - plane * hw4) << 2;     // plane = b * D + z
+    const int64_t b = plane / D, z = plane - b * D;
+    const int64_t chan_stride = (int64_t)D * HW;
+    float *dst0 = canvas + (b * C * D + z) * HW + cell + (int64_t)cq * chan_stride;
+    if (col < total_cols) {
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        float *dst = dst0;
+        for (int c = cq; c < C; c += CV_CGROUPS, dst += CV_CGROUPS * chan_stride) *reinterpret_cast<float4 *>(dst) = zero;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (col >= total_cols) return;
+    const int4 pid = *reinterpret_cast<const int4 *>(map + plane * HW + cell);
+    if ((pid.x & pid.y & pid.z & pid.w) < 0) return;      // all four cells empty (the common case)
+    float *dst = dst0;
+    for (int c = cq; c < C; c += CV_CGROUPS, dst += CV_CGROUPS * chan_stride) {
+        float4 v;
+        v.x = pid.x >= 0 ? __ldg(feat + (int64_t)pid.x * C + c) : 0.f;
+        v.y = pid.y >= 0 ? __ldg(feat + (int64_t)pid.y * C + c) : 0.f;
+        v.z = pid.z >= 0 ? __ldg(feat + (int64_t)pid.z * C + c) : 0.f;
+        v.w = pid.w >= 0 ? __ldg(feat + (int64_t)pid.w * C + c) : 0.f;
+        *reinterpret_cast<float4 *>(dst) = v;
+    }
+}
+
 int fill_pillar_in(PillarIn &a, const float *voxels, const float *in, const void *num, int num_kind, const void *coors,
                    int coors_kind, int64_t M, const int32_t *m_dev, int P, int C, int Cin, float vx, float vy,
                    float x_off, float y_off)
@@ -307,6 +409,8 @@ int fill_pillar_in(PillarIn &a, const float *voxels, const float *in, const void
     a.vx = vx; a.vy = vy; a.x_off = x_off; a.y_off = y_off;
     return 0;
 }
+
+dim3 canvas_wave_grid(int64_t total_cols) { return dim3((unsigned)ceil_div(total_cols, CV_THREADS), CV_CGROUPS); }
 
 unsigned pillar_grid(int64_t M)
 {
@@ -384,10 +488,11 @@ extern "C" int pp_pillar_features(const float *voxels, const void *num_points, i
     PillarIn a;
     fill_pillar_in(a, voxels, nullptr, num_points, num_kind, coors, coors_kind, M, m_dev, P, C, C + 5, vx, vy, x_off,
                    y_off);
-    if (C + 5 <= PFN_LDI && U <= 64) {
-        size_t smem = (size_t)PIL_WARPS * P * PFN_LDI * sizeof(float);
-        PP_REQUIRE(smem <= 48 * 1024, "P too large for the fused PFN kernel");
-        const unsigned grid = pillar_grid(M);
+    if (C + 5 <= PFN_LDI && U <= 64 && P <= 32) {
+        size_t smem = (size_t)PIL_WARPS * 32 * PFN_LDI * sizeof(float);
+        int64_t want = ceil_div(M, PIL_WARPS);
+        // one resident wave that leaves room on every SM for the canvas kernel's early (pre-wait) zero fill
+        const unsigned grid = (unsigned)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
         cudaStream_t st = (cudaStream_t)stream;
         switch (C + 5) {
         case 8: launch_pdl(pfn_fused_small_kernel<8>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
@@ -435,7 +540,10 @@ extern "C" int pp_scatter_dense(const float *feat, const void *coors, int coors_
     }
     const unsigned grid = (unsigned)((int64_t)B * D * tiles_per_plane);
     const bool vec4 = (HW % 4 == 0) && ((uintptr_t)canvas % 16 == 0);
-    if (vec4)
+    if (vec4 && ((uintptr_t)map % 16 == 0))
+        scatter_canvas_wave_kernel<<<canvas_wave_grid((int64_t)B * D * (HW / 4)), CV_THREADS, 0, st>>>(
+            feat, map, C, D, HW, (int64_t)B * D * (HW / 4), canvas);
+    else if (vec4)
         scatter_canvas_kernel<true><<<grid, CANVAS_WARPS * 32, 0, st>>>(feat, map, C, D, HW, (int)tiles_per_plane, canvas);
     else
         scatter_canvas_kernel<false><<<grid, CANVAS_WARPS * 32, 0, st>>>(feat, map, C, D, HW, (int)tiles_per_plane, canvas);
@@ -454,7 +562,10 @@ extern "C" int pp_scatter_mapped(const float *feat, const int32_t *pillar_map, i
     PP_REQUIRE((int64_t)B * D * tiles_per_plane < (1ll << 31), "canvas too large");
     const unsigned grid = (unsigned)((int64_t)B * D * tiles_per_plane);
     const bool vec4 = (HW % 4 == 0) && ((uintptr_t)canvas % 16 == 0);
-    if (vec4)
+    if (vec4 && ((uintptr_t)pillar_map % 16 == 0))
+        launch_pdl(scatter_canvas_wave_kernel, canvas_wave_grid((int64_t)B * D * (HW / 4)), dim3(CV_THREADS), 0, st, feat,
+                   pillar_map, C, D, HW, (int64_t)B * D * (HW / 4), canvas);
+    else if (vec4)
         launch_pdl(scatter_canvas_kernel<true>, dim3(grid), dim3(CANVAS_WARPS * 32), 0, st, feat, pillar_map, C, D, HW,
                    (int)tiles_per_plane, canvas);
     else
