@@ -181,6 +181,14 @@ PP_API int pp_bbox_iou2d(const float *b1, int64_t m, const float *b2, int64_t n,
  * form is the AABB above).  Footprint of a 9-parameter box = centre (x,y), size (dx,dy), yaw rz; (m,9),(n,9) -> (m,n).
  * Sutherland-Hodgman clipping on the FP32 CUDA cores; checked against a float64 oracle (tests/test_rotated_iou.py). */
 PP_API int pp_iou_rotated_bev(const float *b1, int64_t m, const float *b2, int64_t n, float *out, pp_stream_t stream);
+/* box3d_overlap, ops/ops_torch.py:692-755 (pytorch3d _C.iou_box3d, a third-party kernel that is not part of the
+ * reference checkout: parity unpinned; pinned against an independent float64 computation instead).
+ * corners (N,8,3) in the reference's corner order; vol (may be NULL) and iou (N,M).  Exact convex intersection of the
+ * two parallelepipeds (v0; v1-v0, v3-v0, v4-v0), iou = vol / (vol1 + vol2 - vol). */
+PP_API int pp_box3d_overlap(const float *corners1, int64_t n, const float *corners2, int64_t m, float *vol, float *iou,
+                     pp_stream_t stream);
+/* check_coplanar + check_nonzero, ops/ops_torch.py:610-690: flags[i] bit 0 = not coplanar, bit 1 = zero-area face */
+PP_API int pp_box3d_check(const float *corners, int64_t n, float eps, int32_t *flags, pp_stream_t stream);
 /* iou_jit, ops/ops_numba.py:7-36 (eps added to widths, evaluated in f64 like numba) */
 PP_API int pp_iou_jit(const float *boxes, int64_t N, const float *query, int64_t K, double eps, float *out,
                pp_stream_t stream);
@@ -192,7 +200,7 @@ PP_API int pp_iou_jit(const float *boxes, int64_t N, const float *query, int64_t
  * scores: element i at scores[i * score_stride].
  * keep (N) int64: kept ORIGINAL indices in descending-score order; keep_count device int32 scalar.
  */
-enum { PP_NMS_AABB2D = 0, PP_NMS_ROT_BEV = 1 };
+enum { PP_NMS_AABB2D = 0, PP_NMS_ROT_BEV = 1, PP_NMS_BOX3D = 2 };
 PP_API size_t pp_nms_workspace_bytes(int64_t N);
 PP_API int pp_nms(const float *boxes9, const float *scores, int64_t score_stride, int64_t N, float score_thr,
            float iou_thr, int64_t *keep, int32_t *keep_count, void *workspace, size_t workspace_bytes,
@@ -201,7 +209,8 @@ PP_API int pp_nms(const float *boxes9, const float *scores, int64_t score_stride
 /* Same greedy NMS with a selectable pair test.  PP_NMS_AABB2D = pp_nms (the reference's nms_dim == 2 form);
  * PP_NMS_ROT_BEV = rotated BEV footprints (x, y, dx, dy, rz) with the pair IoU of pp_iou_rotated_bev (extension named
  * by the north star, no counterpart in the reference): the footprints' bounding rectangles drive the tile prefilter,
- * polygon clipping runs on the FP32 cores only for pairs whose rectangles overlap. */
+ * polygon clipping runs on the FP32 cores only for pairs whose rectangles overlap.
+ * PP_NMS_BOX3D = the reference's nms_dim == 3 form: oriented 3-D IoU of pp_box3d_overlap on bbox2corners3D(boxes). */
 PP_API size_t pp_nms_workspace_bytes_mode(int64_t N, int iou_mode);
 PP_API int pp_nms_mode(const float *boxes9, const float *scores, int64_t score_stride, int64_t N, float score_thr,
                 float iou_thr, int iou_mode, int64_t *keep, int32_t *keep_count, void *workspace,

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libpp_b200.so")
 
 PP_OK, PP_ERR_INVALID, PP_ERR_CUDA, PP_ERR_WORKSPACE = 0, -1, -2, -3
 ORDER_GIVEN, ORDER_REFLECTANCE_DESC, ORDER_PERM = 0, 1, 2
-NMS_AABB2D, NMS_ROT_BEV = 0, 1
+NMS_AABB2D, NMS_ROT_BEV, NMS_BOX3D = 0, 1, 2
 COORS_XYZ_I32, COORS_BZYX_I32, COORS_BZYX_I64 = 0, 1, 2
 NUM_I32, NUM_I64 = 0, 1
 IOU_MODES = {"iou": 0, "iof": 1, "giou": 2}
@@ -58,6 +58,8 @@ SIGNATURES = {
     "pp_box_aabb2d": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "pp_bbox_iou2d": (ctypes.c_int, [_vp, _i64, _vp, _i64, ctypes.c_int, _f32, _vp, _vp]),
     "pp_iou_rotated_bev": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "pp_box3d_overlap": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "pp_box3d_check": (ctypes.c_int, [_vp, _i64, _f32, _vp, _vp]),
     "pp_iou_jit": (ctypes.c_int, [_vp, _i64, _vp, _i64, _f64, _vp, _vp]),
     "pp_nms_workspace_bytes": (_sz, [_i64]),
     "pp_nms": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),

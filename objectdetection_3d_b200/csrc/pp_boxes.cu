@@ -144,6 +144,86 @@ iou_rot_kernel(const float *__restrict__ b1, int64_t m, const float *__restrict_
     }
 }
 
+// (n,m) oriented 3-D IoU from corners: one thread per column box, 32 row boxes per CTA staged in shared memory
+__global__ void __launch_bounds__(128)
+iou3d_kernel(const float *__restrict__ c1, int64_t n, const float *__restrict__ c2, int64_t m, float *__restrict__ vol,
+             float *__restrict__ iou)
+{
+    __shared__ Box3 s_row[32];
+    __shared__ float4 s_rect[32];
+    const int64_t i0 = (int64_t)blockIdx.y * 32;
+    if (threadIdx.x < 32 && i0 + threadIdx.x < n) {
+        const float *c = c1 + (i0 + threadIdx.x) * 24;
+        s_row[threadIdx.x] = box3_from_corners(c);
+        s_rect[threadIdx.x] = corners_xy_rect(c);
+    }
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (j >= m) return;
+    const Box3 q = box3_from_corners(c2 + j * 24);
+    const float4 qr = corners_xy_rect(c2 + j * 24);
+    for (int r = 0; r < 32 && i0 + r < n; ++r) {
+        // 0 unless the xy bounding rectangles of the corners overlap (the same pre-test the NMS tiles use)
+        float v = 0.f, u = 0.f;
+        const float4 ar = s_rect[r];
+        if (fminf(ar.z, qr.z) > fmaxf(ar.x, qr.x) && fminf(ar.w, qr.w) > fmaxf(ar.y, qr.y)) u = box3_iou(s_row[r], q, &v);
+        if (vol) vol[(i0 + r) * m + j] = v;
+        iou[(i0 + r) * m + j] = u;
+    }
+}
+
+// check_coplanar / check_nonzero, ops/ops_torch.py:610-690: flags bit 0 = fails the coplanarity test, bit 1 = a face
+// triangle with area < eps.  (The reference sums the plane residuals of all six faces before taking the absolute
+// value, :637-641; kept.)
+__device__ __forceinline__ void normalize3(float v[3])
+{
+    const float nrm = fmaxf(sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), 1e-12f);
+    v[0] /= nrm; v[1] /= nrm; v[2] /= nrm;
+}
+__device__ __forceinline__ void cross3(const float a[3], const float b[3], float o[3])
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__global__ void __launch_bounds__(BX_THREADS)
+box3d_check_kernel(const float *__restrict__ corners, int64_t n, float eps, int32_t *__restrict__ flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;
+    if (i >= n) return;
+    float c[8][3];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) c[k / 3][k % 3] = corners[i * 24 + k];
+    const int planes[6][4] = {{0, 1, 2, 3}, {3, 2, 6, 7}, {0, 1, 5, 4}, {0, 3, 7, 4}, {1, 2, 6, 5}, {4, 5, 6, 7}};
+    const int tris[12][3] = {{0, 1, 2}, {0, 3, 2}, {4, 5, 6}, {4, 6, 7}, {1, 5, 6}, {1, 6, 2},
+                             {0, 4, 7}, {0, 7, 3}, {3, 2, 6}, {3, 6, 7}, {0, 1, 5}, {0, 4, 5}};
+    float res = 0.f;
+    for (int p = 0; p < 6; ++p) {
+        float e0[3], e1[3], d[3], nrm[3];
+        for (int k = 0; k < 3; ++k) {
+            e0[k] = c[planes[p][1]][k] - c[planes[p][0]][k];
+            e1[k] = c[planes[p][2]][k] - c[planes[p][0]][k];
+            d[k] = c[planes[p][3]][k] - c[planes[p][0]][k];
+        }
+        normalize3(e0); normalize3(e1);
+        cross3(e0, e1, nrm);
+        normalize3(nrm);
+        res += d[0] * nrm[0] + d[1] * nrm[1] + d[2] * nrm[2];
+    }
+    int f = (fabsf(res) < eps) ? 0 : 1;
+    for (int t = 0; t < 12; ++t) {
+        float a[3], b[3], x[3];
+        for (int k = 0; k < 3; ++k) {
+            a[k] = c[tris[t][1]][k] - c[tris[t][0]][k];
+            b[k] = c[tris[t][2]][k] - c[tris[t][0]][k];
+        }
+        cross3(a, b, x);
+        if (sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]) / 2.f < eps) f |= 2;
+    }
+    flags[i] = f;
+}
+
 __global__ void __launch_bounds__(BX_THREADS)
 iou_jit_kernel(const float *__restrict__ boxes, int64_t N, const float *__restrict__ query, int64_t K, double eps,
                float *__restrict__ out)
@@ -280,4 +360,27 @@ extern "C" int pp_iou_rotated_bev(const float *b1, int64_t m, const float *b2, i
     dim3 grid((unsigned)ceil_div(n, BX_THREADS), (unsigned)ceil_div(m, 32));
     iou_rot_kernel<<<grid, BX_THREADS, 0, (cudaStream_t)stream>>>(b1, m, b2, n, out);
     return check_launch("iou_rot_kernel");
+}
+
+extern "C" int pp_box3d_overlap(const float *corners1, int64_t n, const float *corners2, int64_t m, float *vol, float *iou,
+                                pp_stream_t stream)
+{
+    pp::enter((cudaStream_t)stream);
+    PP_REQUIRE(n >= 0 && m >= 0, "negative size");
+    if (n == 0 || m == 0) return PP_OK;
+    PP_REQUIRE(corners1 && corners2 && iou, "null pointer");
+    PP_REQUIRE(ceil_div(n, 32) < 65536, "too many rows for one launch");
+    dim3 grid((unsigned)ceil_div(m, 128), (unsigned)ceil_div(n, 32));
+    iou3d_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(corners1, n, corners2, m, vol, iou);
+    return check_launch("iou3d_kernel");
+}
+
+extern "C" int pp_box3d_check(const float *corners, int64_t n, float eps, int32_t *flags, pp_stream_t stream)
+{
+    pp::enter((cudaStream_t)stream);
+    PP_REQUIRE(n >= 0, "negative size");
+    if (n == 0) return PP_OK;
+    PP_REQUIRE(corners && flags, "null pointer");
+    box3d_check_kernel<<<(unsigned)ceil_div(n, BX_THREADS), BX_THREADS, 0, (cudaStream_t)stream>>>(corners, n, eps, flags);
+    return check_launch("box3d_check_kernel");
 }

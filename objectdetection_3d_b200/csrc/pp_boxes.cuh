@@ -190,4 +190,194 @@ __device__ __forceinline__ RRect rrect_pack(const float4 lo, const float2 hi)
     return r;
 }
 
+// ---- oriented 3-D boxes (ops/ops_torch.py:692-755 -> pytorch3d _C.iou_box3d; parity unpinned, see oracle) ----------
+// A box is the parallelepiped o = v0, e1 = v1 - v0, e2 = v3 - v0, e3 = v4 - v0 of its 8 corners (reference order).
+struct Box3 {
+    float o[3], e[3][3];
+};
+
+__device__ __forceinline__ Box3 box3_from_corners(const float *c /* (8,3) */)
+{
+    Box3 b;
+    const int nb[3] = {1, 3, 4};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        b.o[k] = c[k];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) b.e[j][k] = c[nb[j] * 3 + k] - c[k];
+    }
+    return b;
+}
+__device__ __forceinline__ Box3 box3_from_corner_array(const float c[8][3])
+{
+    Box3 b;
+    const int nb[3] = {1, 3, 4};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        b.o[k] = c[0][k];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) b.e[j][k] = c[nb[j]][k] - c[0][k];
+    }
+    return b;
+}
+// 12 floats <-> 3 float4
+__device__ __forceinline__ void box3_store(const Box3 &b, float4 &q0, float4 &q1, float4 &q2)
+{
+    q0 = make_float4(b.o[0], b.o[1], b.o[2], b.e[0][0]);
+    q1 = make_float4(b.e[0][1], b.e[0][2], b.e[1][0], b.e[1][1]);
+    q2 = make_float4(b.e[1][2], b.e[2][0], b.e[2][1], b.e[2][2]);
+}
+__device__ __forceinline__ Box3 box3_load(const float4 q0, const float4 q1, const float4 q2)
+{
+    Box3 b;
+    b.o[0] = q0.x; b.o[1] = q0.y; b.o[2] = q0.z; b.e[0][0] = q0.w;
+    b.e[0][1] = q1.x; b.e[0][2] = q1.y; b.e[1][0] = q1.z; b.e[1][1] = q1.w;
+    b.e[1][2] = q2.x; b.e[2][0] = q2.y; b.e[2][1] = q2.z; b.e[2][2] = q2.w;
+    return b;
+}
+
+// xy bounding rectangle of 8 corners stored as (8,3)
+__device__ __forceinline__ float4 corners_xy_rect(const float *c)
+{
+    float x1 = c[0], x2 = c[0], y1 = c[1], y2 = c[1];
+#pragma unroll
+    for (int v = 1; v < 8; ++v) {
+        x1 = fminf(x1, c[v * 3]); x2 = fmaxf(x2, c[v * 3]);
+        y1 = fminf(y1, c[v * 3 + 1]); y2 = fmaxf(y2, c[v * 3 + 1]);
+    }
+    return make_float4(x1, y1, x2, y2);
+}
+
+__device__ __forceinline__ float det3(const float a[3], const float b[3], const float c[3])
+{
+    return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+}
+// rows of the inverse of the matrix whose columns are e[0], e[1], e[2]
+__device__ __forceinline__ void dual3(const float e[3][3], float det, float g[3][3])
+{
+    const float r = 1.f / det;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float *a = e[(k + 1) % 3], *b = e[(k + 2) % 3];
+        g[k][0] = (a[1] * b[2] - a[2] * b[1]) * r;
+        g[k][1] = (a[2] * b[0] - a[0] * b[2]) * r;
+        g[k][2] = (a[0] * b[1] - a[1] * b[0]) * r;
+    }
+}
+
+constexpr int B3_MAXV = 12;
+// keep lo <= g.q + off <= hi (Sutherland-Hodgman, two passes)
+__device__ __forceinline__ int b3_clip(float (*p)[3], int n, const float g[3], float off, float lo, float hi)
+{
+    float q[B3_MAXV][3], s[B3_MAXV];
+#pragma unroll 1
+    for (int pass = 0; pass < 2 && n > 0; ++pass) {
+        const float sgn = pass ? -1.f : 1.f, lim = pass ? -hi : lo;
+        for (int i = 0; i < n; ++i) s[i] = sgn * (g[0] * p[i][0] + g[1] * p[i][1] + g[2] * p[i][2] + off) - lim;
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const int j = (i + 1 == n) ? 0 : i + 1;
+            if (s[i] >= 0.f) { q[m][0] = p[i][0]; q[m][1] = p[i][1]; q[m][2] = p[i][2]; ++m; }
+            if ((s[i] > 0.f && s[j] < 0.f) || (s[i] < 0.f && s[j] > 0.f)) {
+                const float t = s[i] / (s[i] - s[j]);
+                q[m][0] = p[i][0] + t * (p[j][0] - p[i][0]);
+                q[m][1] = p[i][1] + t * (p[j][1] - p[i][1]);
+                q[m][2] = p[i][2] + t * (p[j][2] - p[i][2]);
+                ++m;
+            }
+        }
+        n = m < B3_MAXV ? m : B3_MAXV;
+        for (int i = 0; i < n; ++i) { p[i][0] = q[i][0]; p[i][1] = q[i][1]; p[i][2] = q[i][2]; }
+    }
+    return n;
+}
+// 6 x signed volume of the cone from the origin over the polygon
+__device__ __forceinline__ float b3_cone(float (*p)[3], int n)
+{
+    float v = 0.f;
+    for (int i = 1; i + 1 < n; ++i) v += det3(p[0], p[i], p[i + 1]);
+    return v;
+}
+// face f = 2 * axis + side of the parallelepiped (o; e), outward orientation for a right-handed basis
+__device__ __forceinline__ void b3_face(const float o[3], const float e[3][3], int f, float (*p)[3])
+{
+    const int ax = f >> 1, side = f & 1, a = (ax + 1) % 3, b = (ax + 2) % 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = side ? i : 3 - i;
+        const float ua = (k == 1 || k == 2) ? 1.f : 0.f, ub = (k >= 2) ? 1.f : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p[i][c] = o[c] + (side ? e[ax][c] : 0.f) + ua * e[a][c] + ub * e[b][c];
+    }
+}
+
+// Volume of a ∩ b: a is mapped into b's unit-cube frame (cube centre at the origin); the volume is the sum of the
+// cones over a's faces clipped to the cube (closed slabs) and the cube's faces clipped to a (open slabs).
+__device__ __forceinline__ float box3_inter_volume(const Box3 &a, const Box3 &b, float &va, float &vb)
+{
+    const float eps = 1e-6f;
+    const float d1 = det3(a.e[0], a.e[1], a.e[2]), d2 = det3(b.e[0], b.e[1], b.e[2]);
+    va = fabsf(d1); vb = fabsf(d2);
+    if (!(va > 0.f) || !(vb > 0.f)) return 0.f;
+    float g2[3][3];
+    dual3(b.e, d2, g2);
+    float po[3], pe[3][3];
+    const float dx = a.o[0] - b.o[0], dy = a.o[1] - b.o[1], dz = a.o[2] - b.o[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        po[r] = g2[r][0] * dx + g2[r][1] * dy + g2[r][2] * dz - 0.5f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pe[k][r] = g2[r][0] * a.e[k][0] + g2[r][1] * a.e[k][1] + g2[r][2] * a.e[k][2];
+    }
+    // quick reject: the image of a lies entirely beyond one side of the cube
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float lo = po[r] + fminf(pe[0][r], 0.f) + fminf(pe[1][r], 0.f) + fminf(pe[2][r], 0.f);
+        const float hi = po[r] + fmaxf(pe[0][r], 0.f) + fmaxf(pe[1][r], 0.f) + fmaxf(pe[2][r], 0.f);
+        if (lo >= 0.5f || hi <= -0.5f) return 0.f;
+    }
+    const float dp = det3(pe[0], pe[1], pe[2]);
+    float gp[3][3];
+    dual3(pe, dp, gp);
+    float sum_p = 0.f, sum_c = 0.f, poly[B3_MAXV][3];
+    const float ax[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+#pragma unroll 1
+    for (int f = 0; f < 6; ++f) {
+        b3_face(po, pe, f, poly);
+        int n = 4;
+#pragma unroll 1
+        for (int k = 0; k < 3 && n > 2; ++k) n = b3_clip(poly, n, ax[k], 0.f, -0.5f - eps, 0.5f + eps);
+        if (n > 2) sum_p += b3_cone(poly, n);
+    }
+    const float co[3] = {-0.5f, -0.5f, -0.5f};
+#pragma unroll 1
+    for (int f = 0; f < 6; ++f) {
+        b3_face(co, ax, f, poly);
+        int n = 4;
+#pragma unroll 1
+        for (int k = 0; k < 3 && n > 2; ++k) {
+            const float off = -(gp[k][0] * po[0] + gp[k][1] * po[1] + gp[k][2] * po[2]);
+            n = b3_clip(poly, n, gp[k], off, eps, 1.f - eps);
+        }
+        if (n > 2) sum_c += b3_cone(poly, n);
+    }
+    float v = ((dp < 0.f ? -sum_p : sum_p) + sum_c) * (1.f / 6.f) * vb;
+    v = fmaxf(v, 0.f);
+    return fminf(v, fminf(va, vb));
+}
+
+// Symmetric by construction (canonical argument order), like rrect_iou.
+__device__ __forceinline__ float box3_iou(const Box3 &a, const Box3 &b, float *vol_out)
+{
+    bool swap = false;
+#pragma unroll
+    for (int k = 2; k >= 0; --k)
+        if (a.o[k] != b.o[k]) swap = a.o[k] > b.o[k];
+    float va, vb;
+    const float v = swap ? box3_inter_volume(b, a, vb, va) : box3_inter_volume(a, b, va, vb);
+    if (vol_out) *vol_out = v;
+    const float u = (swap ? vb + va : va + vb) - v;
+    return u > 0.f ? v / u : 0.f;
+}
+
 }  // namespace pp

@@ -22,10 +22,39 @@ enum { SC_N = 0, SC_N1 = 1, SC_K1 = 2, SC_N2 = 3, SC_TICKET = 4, SC_COUNT = 8 };
 constexpr int NMS_LEVEL1 = 2048;   // boxes resolved first; the rest is filtered against their keep set before its own NMS
 constexpr int SWEEP_THREADS = 1024;
 
+// Per-box data of the pair tests that need more than the bounding rectangle: PP_NMS_ROT_BEV uses a0 and a1.xy (RRect),
+// PP_NMS_BOX3D a0..a2 (Box3).
+struct Aux {
+    float4 *a0, *a1, *a2;
+};
+template <int MODE> struct PairGeom;
+template <> struct PairGeom<PP_NMS_AABB2D> {
+    struct T {};
+    static __device__ __forceinline__ T load(const float4 *, const float4 *, const float4 *, int) { return T(); }
+    static __device__ __forceinline__ float iou(const T &, const T &) { return 0.f; }
+};
+template <> struct PairGeom<PP_NMS_ROT_BEV> {
+    typedef RRect T;
+    static __device__ __forceinline__ T load(const float4 *a0, const float4 *a1, const float4 *, int i)
+    {
+        const float4 h = a1[i];
+        return rrect_pack(a0[i], make_float2(h.x, h.y));
+    }
+    static __device__ __forceinline__ float iou(const T &a, const T &b) { return rrect_iou(a, b); }
+};
+template <> struct PairGeom<PP_NMS_BOX3D> {
+    typedef Box3 T;
+    static __device__ __forceinline__ T load(const float4 *a0, const float4 *a1, const float4 *a2, int i)
+    {
+        return box3_load(a0[i], a1[i], a2[i]);
+    }
+    static __device__ __forceinline__ float iou(const T &a, const T &b) { return box3_iou(a, b, nullptr); }
+};
+
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, int64_t stride, int64_t N,
                    float score_thr, float4 *__restrict__ rect, uint32_t *__restrict__ keys, int32_t *__restrict__ n_cand,
-                   float4 *__restrict__ rr_lo, float2 *__restrict__ rr_hi)
+                   int mode, const Aux aux)
 {
     int64_t i = (int64_t)blockIdx.x * NMS_THREADS + threadIdx.x;
     bool cand = false;
@@ -33,16 +62,21 @@ nms_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ sc
         float b[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) b[k] = boxes[i * 9 + k];
-        if (rr_lo) {
-            // PP_NMS_ROT_BEV: rotated footprint (x, y, dx, dy, rz); its bounding rectangle drives the prefilter
+        if (mode == PP_NMS_ROT_BEV) {
+            // rotated footprint (x, y, dx, dy, rz); its bounding rectangle drives the prefilter
             const RRect r = rrect_from_box9(b);
             rect[i] = rrect_aabb(r);
-            rr_lo[i] = rrect_lo(r);
-            rr_hi[i] = rrect_hi(r);
+            aux.a0[i] = rrect_lo(r);
+            aux.a1[i] = make_float4(r.c, r.s, 0.f, 0.f);
         } else {
             float c[8][3];
             box_corners(b, c);
             rect[i] = corners_to_rect(c);
+            if (mode == PP_NMS_BOX3D) {
+                float4 q0, q1, q2;
+                box3_store(box3_from_corner_array(c), q0, q1, q2);
+                aux.a0[i] = q0; aux.a1[i] = q1; aux.a2[i] = q2;
+            }
         }
         float s = scores[i * stride];
         cand = s > score_thr;
@@ -54,8 +88,7 @@ nms_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ sc
 
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_gather_kernel(const float4 *__restrict__ rect, const uint32_t *__restrict__ order, int32_t *__restrict__ sc,
-                  float4 *__restrict__ srect, int level1, const float4 *__restrict__ rr_lo,
-                  const float2 *__restrict__ rr_hi, float4 *__restrict__ srr_lo, float2 *__restrict__ srr_hi)
+                  float4 *__restrict__ srect, int level1, const Aux aux, const Aux saux)
 {
     int64_t r = (int64_t)blockIdx.x * NMS_THREADS + threadIdx.x;
     const int n = sc[SC_N];
@@ -63,7 +96,8 @@ nms_gather_kernel(const float4 *__restrict__ rect, const uint32_t *__restrict__ 
     if (r < n) {
         const uint32_t o = order[r];
         srect[r] = rect[o];
-        if (rr_lo) { srr_lo[r] = rr_lo[o]; srr_hi[r] = rr_hi[o]; }
+        if (aux.a0) { saux.a0[r] = aux.a0[o]; saux.a1[r] = aux.a1[o]; }
+        if (aux.a2) saux.a2[r] = aux.a2[o];
     }
 }
 
@@ -94,16 +128,17 @@ __device__ __forceinline__ uint2 rect_to_half(const float4 r)
 template <bool PREFILTER, int MODE>
 __global__ void __launch_bounds__(MT_ROWS)
 nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_cand, float thr, int nw_stride,
-                u64 *__restrict__ mask, u64 *__restrict__ band, const float4 *__restrict__ srr_lo,
-                const float2 *__restrict__ srr_hi)
+                u64 *__restrict__ mask, u64 *__restrict__ band, const Aux saux)
 {
+    typedef PairGeom<MODE> G;
     const int n = *n_cand;
     const int row0 = blockIdx.y * MT_ROWS, col0 = blockIdx.x * MT_COLS;
     if (row0 >= n || col0 >= n || col0 + MT_COLS <= row0) return;
     __shared__ float4 s_col[MT_COLS];
     __shared__ uint2 s_colh[MT_COLS];     // the same rectangles as conservative half2 pairs: (x1,y1) down, (x2,y2) up
-    __shared__ float4 s_rlo[MODE == PP_NMS_ROT_BEV ? MT_COLS : 1];     // rotated footprints of the column boxes
-    __shared__ float2 s_rhi[MODE == PP_NMS_ROT_BEV ? MT_COLS : 1];
+    __shared__ float4 s_a0[MODE != PP_NMS_AABB2D ? MT_COLS : 1];       // per-box geometry of the column boxes
+    __shared__ float4 s_a1[MODE != PP_NMS_AABB2D ? MT_COLS : 1];
+    __shared__ float4 s_a2[MODE == PP_NMS_BOX3D ? MT_COLS : 1];
     const int t = threadIdx.x;
 #pragma unroll
     for (int k = 0; k < MT_COLS / MT_ROWS; ++k) {
@@ -112,9 +147,10 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
         const float4 q = c < n ? srect[c] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
         s_col[t + k * MT_ROWS] = q;
         s_colh[t + k * MT_ROWS] = rect_to_half(q);
-        if (MODE == PP_NMS_ROT_BEV && c < n) {
-            s_rlo[t + k * MT_ROWS] = srr_lo[c];
-            s_rhi[t + k * MT_ROWS] = srr_hi[c];
+        if (MODE != PP_NMS_AABB2D && c < n) {
+            s_a0[t + k * MT_ROWS] = saux.a0[c];
+            s_a1[t + k * MT_ROWS] = saux.a1[c];
+            if (MODE == PP_NMS_BOX3D) s_a2[t + k * MT_ROWS] = saux.a2[c];
         }
     }
     __syncthreads();
@@ -122,8 +158,8 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
     if (i >= n) return;
     const float4 a = srect[i];
     const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-    RRect ra;
-    if (MODE == PP_NMS_ROT_BEV) ra = rrect_pack(srr_lo[i], srr_hi[i]);
+    typename G::T ga;
+    if (MODE != PP_NMS_AABB2D) ga = G::load(saux.a0, saux.a1, saux.a2, i);
     const uint2 ah = rect_to_half(a);
     const __half2 a_lo = *reinterpret_cast<const __half2 *>(&ah.x), a_hi = *reinterpret_cast<const __half2 *>(&ah.y);
 #pragma unroll 1
@@ -163,12 +199,12 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
             cand &= cand - 1;
             const float4 q = s_col[wd * 64 + j];
             bool hit;
-            if (MODE == PP_NMS_ROT_BEV) {
-                // same definition as pp_iou_rotated_bev: 0 unless the fp32 bounding rectangles overlap, else the
-                // clipped-polygon IoU (symmetric in its arguments)
+            if (MODE != PP_NMS_AABB2D) {
+                // same definition as pp_iou_rotated_bev / pp_box3d_overlap: 0 unless the fp32 xy bounding rectangles
+                // overlap, else the clipped-polygon (polyhedron) IoU, symmetric in its arguments
                 float v = 0.f;
                 if (fminf(a.z, q.z) > fmaxf(a.x, q.x) && fminf(a.w, q.w) > fmaxf(a.y, q.y))
-                    v = rrect_iou(rrect_pack(s_rlo[wd * 64 + j], s_rhi[wd * 64 + j]), ra);
+                    v = G::iou(G::load(s_a0, s_a1, s_a2, wd * 64 + j), ga);
                 hit = v > thr;
             } else if (PREFILTER) {
                 // iou > thr  <=>  overlap > thr * union, decided without the division unless the two sides are
@@ -381,12 +417,13 @@ template <int MODE>
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__ order, int32_t *__restrict__ sc,
                   const int32_t *__restrict__ kept_rank, float thr, float4 *__restrict__ srect2,
-                  uint32_t *__restrict__ order2, uint32_t *status, const float4 *__restrict__ srr_lo,
-                  const float2 *__restrict__ srr_hi, float4 *__restrict__ srr2_lo, float2 *__restrict__ srr2_hi)
+                  uint32_t *__restrict__ order2, uint32_t *status, const Aux saux, const Aux saux2)
 {
+    typedef PairGeom<MODE> G;
     __shared__ float4 s_k[NMS_THREADS];
-    __shared__ float4 s_klo[MODE == PP_NMS_ROT_BEV ? NMS_THREADS : 1];
-    __shared__ float2 s_khi[MODE == PP_NMS_ROT_BEV ? NMS_THREADS : 1];
+    __shared__ float4 s_k0[MODE != PP_NMS_AABB2D ? NMS_THREADS : 1];
+    __shared__ float4 s_k1[MODE != PP_NMS_AABB2D ? NMS_THREADS : 1];
+    __shared__ float4 s_k2[MODE == PP_NMS_BOX3D ? NMS_THREADS : 1];
     __shared__ uint32_t s_tile, s_excl;
     __shared__ uint32_t s_warp[NMS_THREADS / 32];
     __shared__ unsigned char s_dead[FLT_BOXES];
@@ -402,15 +439,16 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
     const int r = n1 + (int)tile * FLT_BOXES + bi;
     const bool valid = r < n;
     const float4 box = valid ? srect[r] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
-    RRect rbox;
-    if (MODE == PP_NMS_ROT_BEV && valid) rbox = rrect_pack(srr_lo[r], srr_hi[r]);
+    typename G::T gbox;
+    if (MODE != PP_NMS_AABB2D && valid) gbox = G::load(saux.a0, saux.a1, saux.a2, r);
     const bool zero_hits = 0.f > thr;
     bool dead = false;
     for (int k0 = 0; k0 < k1; k0 += NMS_THREADS) {
         if (k0 + tid < k1) {
             const int kr = kept_rank[k0 + tid];
             s_k[tid] = srect[kr];
-            if (MODE == PP_NMS_ROT_BEV) { s_klo[tid] = srr_lo[kr]; s_khi[tid] = srr_hi[kr]; }
+            if (MODE != PP_NMS_AABB2D) { s_k0[tid] = saux.a0[kr]; s_k1[tid] = saux.a1[kr]; }
+            if (MODE == PP_NMS_BOX3D) s_k2[tid] = saux.a2[kr];
         }
         __syncthreads();
         const int kn = min(NMS_THREADS, k1 - k0);
@@ -421,7 +459,7 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
                 const bool apart = !(fminf(box.z, q.z) > fmaxf(box.x, q.x) && fminf(box.w, q.w) > fmaxf(box.y, q.y));
                 bool hit;
                 if (apart) hit = zero_hits;
-                else if (MODE == PP_NMS_ROT_BEV) hit = rrect_iou(rbox, rrect_pack(s_klo[j], s_khi[j])) > thr;
+                else if (MODE != PP_NMS_AABB2D) hit = G::iou(gbox, G::load(s_k0, s_k1, s_k2, j)) > thr;
                 else hit = rect_iou(box, q, 0, 1e-6f) > thr;
                 if (hit) { dead = true; break; }
             }
@@ -467,7 +505,8 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
         const uint32_t pos = s_excl + wbase + __popc(bal & lanemask_lt());
         srect2[pos] = srect[rr];
         order2[pos] = order[rr];
-        if (MODE == PP_NMS_ROT_BEV) { srr2_lo[pos] = srr_lo[rr]; srr2_hi[pos] = srr_hi[rr]; }
+        if (MODE != PP_NMS_AABB2D) { saux2.a0[pos] = saux.a0[rr]; saux2.a1[pos] = saux.a1[rr]; }
+        if (MODE == PP_NMS_BOX3D) saux2.a2[pos] = saux.a2[rr];
     }
 }
 
@@ -479,8 +518,7 @@ struct NmsWs {
     float4 *rect, *srect, *srect2;
     uint32_t *keys, *keys_sorted, *order, *order2;
     int32_t *kept_rank;
-    float4 *rr_lo, *srr_lo, *srr2_lo;      // PP_NMS_ROT_BEV only
-    float2 *rr_hi, *srr_hi, *srr2_hi;
+    Aux aux, saux, saux2;                  // unsorted / sorted / level-2 geometry (modes other than AABB2D)
     u64 *mask1, *mask2;
     void *sort_ws;
     size_t sort_ws_bytes;
@@ -509,13 +547,12 @@ NmsWs carve(void *ws, int64_t N, int mode, size_t *total)
     w.order = a.take<uint32_t>((size_t)n1);
     w.order2 = a.take<uint32_t>((size_t)(l2 > 0 ? l2 : 1));
     w.kept_rank = a.take<int32_t>((size_t)l1);
-    const bool rot = mode == PP_NMS_ROT_BEV;
-    w.rr_lo = rot ? a.take<float4>((size_t)n1) : nullptr;
-    w.srr_lo = rot ? a.take<float4>((size_t)n1) : nullptr;
-    w.srr2_lo = rot ? a.take<float4>((size_t)(l2 > 0 ? l2 : 1)) : nullptr;
-    w.rr_hi = rot ? a.take<float2>((size_t)n1) : nullptr;
-    w.srr_hi = rot ? a.take<float2>((size_t)n1) : nullptr;
-    w.srr2_hi = rot ? a.take<float2>((size_t)(l2 > 0 ? l2 : 1)) : nullptr;
+    const int naux = mode == PP_NMS_BOX3D ? 3 : (mode == PP_NMS_ROT_BEV ? 2 : 0);
+    float4 **slots[3][3] = {{&w.aux.a0, &w.aux.a1, &w.aux.a2}, {&w.saux.a0, &w.saux.a1, &w.saux.a2},
+                            {&w.saux2.a0, &w.saux2.a1, &w.saux2.a2}};
+    for (int g = 0; g < 3; ++g)
+        for (int k = 0; k < 3; ++k)
+            *slots[g][k] = k < naux ? a.take<float4>((size_t)(g == 2 ? (l2 > 0 ? l2 : 1) : n1)) : nullptr;
     w.mask1 = a.take<u64>((size_t)l1 * w.nw1);
     w.mask2 = a.take<u64>(l2 > 0 ? (size_t)l2 * w.nw2 : 1);
     w.sort_ws_bytes = sort_workspace_bytes(n1);
@@ -526,19 +563,15 @@ NmsWs carve(void *ws, int64_t N, int mode, size_t *total)
 
 int launch_level(const float4 *rects, const int32_t *n_ptr, int64_t n_max, float thr, int nw, u64 *mask, u64 *band,
                  const uint32_t *order, int64_t *keep, const int32_t *keep_base, int32_t *keep_count,
-                 int32_t *kept_rank, int32_t *kept_n, const float4 *rr_lo, const float2 *rr_hi, cudaStream_t st)
+                 int32_t *kept_rank, int32_t *kept_n, int mode, const Aux saux, cudaStream_t st)
 {
     dim3 grid((unsigned)ceil_div(n_max, MT_COLS), (unsigned)ceil_div(n_max, MT_ROWS));
     // thr >= 0: a pair whose bounding rectangles are apart has iou == 0, which only exceeds a negative threshold
-    if (rr_lo) {
-        if (thr >= 0.f)
-            nms_mask_kernel<true, PP_NMS_ROT_BEV><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, rr_lo, rr_hi);
-        else
-            nms_mask_kernel<false, PP_NMS_ROT_BEV><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, rr_lo, rr_hi);
-    } else if (thr >= 0.f)
-        nms_mask_kernel<true, PP_NMS_AABB2D><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, nullptr, nullptr);
-    else
-        nms_mask_kernel<false, PP_NMS_AABB2D><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, nullptr, nullptr);
+#define PP_MASK(PF, MD) nms_mask_kernel<PF, MD><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, saux)
+    if (mode == PP_NMS_BOX3D) { if (thr >= 0.f) PP_MASK(true, PP_NMS_BOX3D); else PP_MASK(false, PP_NMS_BOX3D); }
+    else if (mode == PP_NMS_ROT_BEV) { if (thr >= 0.f) PP_MASK(true, PP_NMS_ROT_BEV); else PP_MASK(false, PP_NMS_ROT_BEV); }
+    else { if (thr >= 0.f) PP_MASK(true, PP_NMS_AABB2D); else PP_MASK(false, PP_NMS_AABB2D); }
+#undef PP_MASK
     if (int rc = check_launch("nms_mask_kernel")) return rc;
     const size_t smem = ((size_t)SW_RING * SW_BAND + 3 * (size_t)nw) * sizeof(u64) + (size_t)nw * sizeof(int);
     PP_REQUIRE(smem <= 96 * 1024, "too many boxes for the sweep's shared memory");
@@ -569,7 +602,7 @@ extern "C" int pp_nms_mode(const float *boxes9, const float *scores, int64_t sco
     cudaStream_t st = (cudaStream_t)stream;
     PP_REQUIRE(keep_count, "null keep_count");
     PP_REQUIRE(N >= 0 && N <= 131072, "N must be in [0, 131072]");
-    PP_REQUIRE(iou_mode == PP_NMS_AABB2D || iou_mode == PP_NMS_ROT_BEV, "unknown iou_mode");
+    PP_REQUIRE(iou_mode == PP_NMS_AABB2D || iou_mode == PP_NMS_ROT_BEV || iou_mode == PP_NMS_BOX3D, "unknown iou_mode");
     if (N == 0) {
         PP_CUDA_TRY(cudaMemsetAsync(keep_count, 0, sizeof(int32_t), st));
         return PP_OK;
@@ -591,31 +624,29 @@ extern "C" int pp_nms_mode(const float *boxes9, const float *scores, int64_t sco
     }
     const unsigned nb = (unsigned)ceil_div(N, NMS_THREADS);
     nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.sc + SC_N,
-                                                   w.rr_lo, w.rr_hi);
+                                                   iou_mode, w.aux);
     if (int rc = check_launch("nms_prepare_kernel")) return rc;
     if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st)) return rc;
-    nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.sc, w.srect, NMS_LEVEL1, w.rr_lo, w.rr_hi, w.srr_lo,
-                                                  w.srr_hi);
+    nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.sc, w.srect, NMS_LEVEL1, w.aux, w.saux);
     if (int rc = check_launch("nms_gather_kernel")) return rc;
     // level 1: greedy NMS of the NMS_LEVEL1 best-scored candidates
     const int64_t l1 = N < NMS_LEVEL1 ? N : NMS_LEVEL1;
     if (int rc = launch_level(w.srect, w.sc + SC_N1, l1, iou_thr, w.nw1, w.mask1, w.band1, w.order, keep, nullptr,
-                              keep_count, w.kept_rank, w.sc + SC_K1, w.srr_lo, w.srr_hi, st))
+                              keep_count, w.kept_rank, w.sc + SC_K1, iou_mode, w.saux, st))
         return rc;
     if (N <= NMS_LEVEL1) return PP_OK;
     // the other candidates: drop those suppressed by level 1's keep set, compact in rank order, NMS among themselves
     const int64_t l2 = N - NMS_LEVEL1;
     const unsigned fb = (unsigned)ceil_div(l2, FLT_BOXES);
-    if (iou_mode == PP_NMS_ROT_BEV)
-        nms_filter_kernel<PP_NMS_ROT_BEV><<<fb, NMS_THREADS, 0, st>>>(w.srect, w.order, w.sc, w.kept_rank, iou_thr, w.srect2,
-                                                                       w.order2, w.status, w.srr_lo, w.srr_hi, w.srr2_lo,
-                                                                       w.srr2_hi);
-    else
-        nms_filter_kernel<PP_NMS_AABB2D><<<fb, NMS_THREADS, 0, st>>>(w.srect, w.order, w.sc, w.kept_rank, iou_thr, w.srect2,
-                                                                      w.order2, w.status, nullptr, nullptr, nullptr, nullptr);
+#define PP_FILTER(MD) nms_filter_kernel<MD><<<fb, NMS_THREADS, 0, st>>>(w.srect, w.order, w.sc, w.kept_rank, iou_thr, w.srect2, \
+                                                                       w.order2, w.status, w.saux, w.saux2)
+    if (iou_mode == PP_NMS_BOX3D) PP_FILTER(PP_NMS_BOX3D);
+    else if (iou_mode == PP_NMS_ROT_BEV) PP_FILTER(PP_NMS_ROT_BEV);
+    else PP_FILTER(PP_NMS_AABB2D);
+#undef PP_FILTER
     if (int rc = check_launch("nms_filter_kernel")) return rc;
     return launch_level(w.srect2, w.sc + SC_N2, l2, iou_thr, w.nw2, w.mask2, w.band2, w.order2, keep, w.sc + SC_K1,
-                        keep_count, nullptr, nullptr, w.srr2_lo, w.srr2_hi, st);
+                        keep_count, nullptr, nullptr, iou_mode, w.saux2, st);
 }
 
 extern "C" int pp_nms(const float *boxes9, const float *scores, int64_t score_stride, int64_t N, float score_thr,

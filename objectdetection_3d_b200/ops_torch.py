@@ -61,8 +61,52 @@ def bbox_iou_rotated_bev(bboxes1, bboxes2):
     return out
 
 
-def box3d_overlap(boxes1, boxes2, eps=1e-2):
-    """ops/ops_torch.py:711-755 (pytorch3d oriented 3-D IoU).  Out of the pinned scope: SURVEY.md
-    section 8(f) rank 1 ("next"); the reference's own implementation lives in an absent third-party
-    library, so there is no oracle to pin it against yet."""
-    raise NotImplementedError("BOX3D oriented IoU is not built yet (SURVEY.md 8f); use nms_dim=2")
+def _box3d_flags(boxes, eps):
+    c = _f32c(boxes)
+    flags = torch.empty((c.shape[0],), dtype=torch.int32, device=c.device)
+    if c.shape[0]:
+        _lib.check(_lib.load().pp_box3d_check(_ptr(c), c.shape[0], float(eps), _ptr(flags), _stream()))
+    return flags
+
+
+def check_coplanar(boxes, eps=1e-4):
+    """ops/ops_torch.py:610-648: raises ValueError when the plane residual test fails for any box."""
+    bad = (_box3d_flags(boxes, eps) & 1) != 0
+    if bad.any().item():
+        raise ValueError("Plane vertices are not coplanar. This applies for bboxes in positions: {}".format(
+            torch.arange(0, boxes.shape[0])[bad.cpu()]))
+
+
+def check_nonzero(boxes, eps=1e-4):
+    """ops/ops_torch.py:651-690: raises ValueError when a face triangle of any box has area < eps."""
+    bad = (_box3d_flags(boxes, eps) & 2) != 0
+    if bad.any().item():
+        raise ValueError("Planes have zero areas. This applies for bboxes in positions: {}".format(
+            torch.arange(0, boxes.shape[0])[bad.cpu()]))
+
+
+def box3d_overlap(boxes1, boxes2, eps=1e-2, return_vol=False):
+    """ops/ops_torch.py:711-755: oriented 3-D IoU of boxes given by their 8 corners, (N,8,3),(M,8,3) -> iou (N,M)
+    (the reference returns only the IoU, :753-755).  The reference delegates to pytorch3d 0.7.4 `_C.iou_box3d`, which is
+    not part of its checkout: this kernel computes the exact convex intersection volume of the two boxes (taken as
+    the parallelepipeds v0; v1-v0, v3-v0, v4-v0) and is validated against an independent float64 computation
+    (tests/test_box3d.py), not against pytorch3d.  Same ValueError behaviour as the reference's validity checks."""
+    if not all((8, 3) == tuple(box.shape[1:]) for box in [boxes1, boxes2]):
+        raise ValueError("Each box in the batch must be of shape (8, 3)")
+    c1, c2 = _f32c(boxes1), _f32c(boxes2)
+    for c in (c1, c2):                       # one flag kernel + one sync per operand (the reference: two each)
+        fl = _box3d_flags(c, eps)
+        nc, nz = (fl & 1) != 0, (fl & 2) != 0
+        if nc.any().item():
+            raise ValueError("Plane vertices are not coplanar. This applies for bboxes in positions: {}".format(
+                torch.arange(0, c.shape[0])[nc.cpu()]))
+        if nz.any().item():
+            raise ValueError("Planes have zero areas. This applies for bboxes in positions: {}".format(
+                torch.arange(0, c.shape[0])[nz.cpu()]))
+    n, m = c1.shape[0], c2.shape[0]
+    iou = torch.empty((n, m), dtype=torch.float32, device=c1.device)
+    vol = torch.empty((n, m), dtype=torch.float32, device=c1.device) if return_vol else None
+    if n * m:
+        _lib.check(_lib.load().pp_box3d_overlap(_ptr(c1), n, _ptr(c2), m, _ptr(vol) if return_vol else None, _ptr(iou),
+                                                _stream()))
+    return (vol, iou) if return_vol else iou

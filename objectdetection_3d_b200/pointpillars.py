@@ -15,7 +15,7 @@ from torch.nn import functional as F
 from . import _lib
 from .model_utils import Anchor3DRangeGenerator, BBoxCoder, limit_period, multiclass_nms
 from .ops_numba import VoxelGenerator, _ptr, _stream, voxel_cfg, voxelize_device
-from .ops_torch import bbox2rotated_corners2D, bbox_iou2D
+from .ops_torch import bbox2corners3D, bbox2rotated_corners2D, bbox_iou2D, box3d_overlap
 
 
 class PointPillarsVoxelization(nn.Module):
@@ -285,14 +285,16 @@ class Anchor3DHead(nn.Module):
 
     # ---- training targets: :886-1000 ------------------------------------------------------------
     def assign_bboxes(self, pred_bboxes, target_bboxes):
-        if self.nms_dim != 2:
-            raise NotImplementedError("nms_dim=3 needs the BOX3D IoU (SURVEY.md 8f)")
         dev = pred_bboxes.device
         anchors = self.anchor_generator.grid_anchors(pred_bboxes.shape[-2:], device=dev)
         anchors_cnt = int(np.prod(anchors.shape[:-1]))
         rot_angles = anchors.shape[-2]
         flat = anchors.reshape(-1, self.box_params_num)
-        anchor_rect = bbox2rotated_corners2D(flat)
+        if self.nms_dim == 3:
+            box2vertices, box_overlap = bbox2corners3D, box3d_overlap          # :899-901
+        else:
+            box2vertices, box_overlap = bbox2rotated_corners2D, bbox_iou2D     # :903-905
+        anchor_rect = box2vertices(flat)
         assigned, target_idxs, pos_idxs, neg_idxs = [], [], [], []
 
         def flatten_idx(idx, j):
@@ -307,7 +309,7 @@ class Anchor3DHead(nn.Module):
                     for lst in (target_idxs, pos_idxs, neg_idxs):
                         lst.append(torch.zeros((0,), dtype=torch.long, device=dev))
                     continue
-                overlaps = bbox_iou2D(bbox2rotated_corners2D(gts), anchor_rect)          # :964-965
+                overlaps = box_overlap(box2vertices(gts), anchor_rect)          # :964-965
                 max_ov, argmax_ov = overlaps.max(dim=0)
                 gt_max, _ = overlaps.max(dim=1)
                 lo, hi = self.iou_thr[j]

@@ -261,3 +261,14 @@ def bbox_iou_rotated_bev(b1, b2):
     lib().ppo_iou_rotated_bev(_p(b1, c_f32p), ctypes.c_int64(b1.shape[0]), _p(b2, c_f32p), ctypes.c_int64(b2.shape[0]),
                               _p(out, c_f64p))
     return out
+
+
+def box3d_overlap(c1, c2):
+    """Oriented 3-D box intersection volume and IoU from corners (n,8,3),(m,8,3), float64.  PARITY UNPINNED against
+    the reference (pytorch3d _C.iou_box3d is absent); pinned against scipy in tests/test_box3d.py."""
+    c1, c2 = _f32(c1).reshape(-1, 24), _f32(c2).reshape(-1, 24)
+    vol = np.empty((c1.shape[0], c2.shape[0]), dtype=np.float64)
+    iou = np.empty_like(vol)
+    lib().ppo_box3d_overlap(_p(c1, c_f32p), ctypes.c_int64(c1.shape[0]), _p(c2, c_f32p), ctypes.c_int64(c2.shape[0]),
+                            _p(vol, c_f64p), _p(iou, c_f64p))
+    return vol, iou
