@@ -216,6 +216,17 @@ PP_API int pp_nms_mode(const float *boxes9, const float *scores, int64_t score_s
                 float iou_thr, int iou_mode, int64_t *keep, int32_t *keep_count, void *workspace,
                 size_t workspace_bytes, pp_stream_t stream);
 
+/*
+ * Target assignment reductions of Anchor3DHead.assign_bboxes, model/PointPillars.py:964-978, without the (G, A)
+ * IoU matrix: for every anchor the best IoU over the ground truths and the FIRST ground truth reaching it (:968),
+ * for every ground truth its best IoU over the anchors (:971), and the low-quality-match flag (:976-978):
+ * lowq[a] = any g with gt_max[g] >= lo_thr and iou(g, a) == gt_max[g].
+ * iou_mode PP_NMS_AABB2D: gt (G,4), anchors (A,4) rectangles (bbox2rotated_corners2D outputs, bbox_iou2D pair test);
+ * PP_NMS_BOX3D: gt (G,8,3), anchors (A,8,3) corners (bbox2corners3D outputs, box3d_overlap pair test).
+ */
+PP_API int pp_assign_overlaps(const float *gt, int64_t G, const float *anchors, int64_t A, int iou_mode, float lo_thr,
+                       float *max_ov, int32_t *argmax, float *gt_max, uint8_t *lowq, pp_stream_t stream);
+
 /* Stable radix sort of (u32 key, u32 value) pairs, ascending; building block exposed for tests. */
 PP_API size_t pp_sort_workspace_bytes(int64_t n);
 PP_API int pp_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out,

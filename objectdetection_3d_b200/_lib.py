@@ -60,6 +60,7 @@ SIGNATURES = {
     "pp_iou_rotated_bev": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "pp_box3d_overlap": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "pp_box3d_check": (ctypes.c_int, [_vp, _i64, _f32, _vp, _vp]),
+    "pp_assign_overlaps": (ctypes.c_int, [_vp, _i64, _vp, _i64, ctypes.c_int, _f32, _vp, _vp, _vp, _vp, _vp]),
     "pp_iou_jit": (ctypes.c_int, [_vp, _i64, _vp, _i64, _f64, _vp, _vp]),
     "pp_nms_workspace_bytes": (_sz, [_i64]),
     "pp_nms": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),

@@ -224,6 +224,88 @@ box3d_check_kernel(const float *__restrict__ corners, int64_t n, float eps, int3
     flags[i] = f;
 }
 
+// ---- target assignment, Anchor3DHead.assign_bboxes (model/PointPillars.py:964-978) -------------------------------
+// IoU(ground truths x anchors) fused with its two reductions, so the (G, A) matrix (hundreds of MB at the reference's
+// map sizes) is never stored.  Pass 1: per anchor max / first argmax over the ground truths (:968) and per ground
+// truth max over the anchors (:971); pass 2: low-quality matching (:976-978), the anchors that tie a ground truth's
+// best IoU -- the pair IoU is recomputed, which is bit-identical, so `==` means what it means in the reference.
+constexpr int AS_THREADS = 256;
+constexpr int AS_GT = 64;          // ground truths staged per pass
+
+template <int MODE> struct AssignGeom;
+template <> struct AssignGeom<PP_NMS_AABB2D> {
+    typedef float4 T;
+    static __device__ __forceinline__ T load(const float *p, int64_t i) { return reinterpret_cast<const float4 *>(p)[i]; }
+    // bbox_iou2D(bboxes1 = ground truths, bboxes2 = anchors)
+    static __device__ __forceinline__ float iou(const T &gt, const T &an) { return rect_iou(gt, an, 0, 1e-6f); }
+};
+template <> struct AssignGeom<PP_NMS_BOX3D> {
+    struct T { Box3 b; float4 r; };
+    static __device__ __forceinline__ T load(const float *p, int64_t i)
+    {
+        T t;
+        t.b = box3_from_corners(p + i * 24);
+        t.r = corners_xy_rect(p + i * 24);
+        return t;
+    }
+    static __device__ __forceinline__ float iou(const T &gt, const T &an)
+    {
+        if (!(fminf(gt.r.z, an.r.z) > fmaxf(gt.r.x, an.r.x) && fminf(gt.r.w, an.r.w) > fmaxf(gt.r.y, an.r.y))) return 0.f;
+        return box3_iou(gt.b, an.b, nullptr);
+    }
+};
+
+template <int MODE, bool LOWQ>
+__global__ void __launch_bounds__(AS_THREADS)
+assign_kernel(const float *__restrict__ gt, int G, const float *__restrict__ anchors, int64_t A, float lo_thr,
+              float *__restrict__ max_ov, int32_t *__restrict__ argmax, float *gt_max, uint8_t *__restrict__ lowq)
+{
+    typedef AssignGeom<MODE> Geo;
+    __shared__ typename Geo::T s_gt[AS_GT];
+    __shared__ float s_gmax[AS_GT];
+    const int64_t a = (int64_t)blockIdx.x * AS_THREADS + threadIdx.x;
+    const bool valid = a < A;
+    typename Geo::T an;
+    if (valid) an = Geo::load(anchors, a);
+    float best = -1.f;
+    int best_g = 0;
+    bool flag = false;
+    for (int g0 = 0; g0 < G; g0 += AS_GT) {
+        const int gn = min(AS_GT, G - g0);
+        __syncthreads();
+        if ((int)threadIdx.x < gn) {
+            s_gt[threadIdx.x] = Geo::load(gt, g0 + threadIdx.x);
+            s_gmax[threadIdx.x] = LOWQ ? gt_max[g0 + threadIdx.x] : 0.f;
+        }
+        __syncthreads();
+        for (int g = 0; g < gn; ++g) {
+            if (LOWQ) {
+                const float gm = s_gmax[g];
+                if (!(gm >= lo_thr)) continue;                             // :977 (CTA-uniform)
+                if (valid && Geo::iou(s_gt[g], an) == gm) flag = true;      // :978
+            } else {
+                const float v = valid ? Geo::iou(s_gt[g], an) : 0.f;
+                if (v > best) { best = v; best_g = g0 + g; }               // first maximum
+                // IoU >= 0: the float order equals the order of the bit patterns
+                const unsigned wmax = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(v));
+                if (wmax != 0u && (threadIdx.x & 31) == 0) atomicMax((unsigned *)&s_gmax[g], wmax);
+            }
+        }
+        if (!LOWQ) {
+            __syncthreads();
+            if ((int)threadIdx.x < gn && __float_as_uint(s_gmax[threadIdx.x]) != 0u)
+                atomicMax((unsigned *)(gt_max + g0 + threadIdx.x), __float_as_uint(s_gmax[threadIdx.x]));
+        }
+    }
+    if (!valid) return;
+    if (LOWQ) {
+        lowq[a] = flag ? 1 : 0;
+    } else {
+        max_ov[a] = best;
+        argmax[a] = best_g;
+    }
+}
+
 __global__ void __launch_bounds__(BX_THREADS)
 iou_jit_kernel(const float *__restrict__ boxes, int64_t N, const float *__restrict__ query, int64_t K, double eps,
                float *__restrict__ out)
@@ -383,4 +465,30 @@ extern "C" int pp_box3d_check(const float *corners, int64_t n, float eps, int32_
     PP_REQUIRE(corners && flags, "null pointer");
     box3d_check_kernel<<<(unsigned)ceil_div(n, BX_THREADS), BX_THREADS, 0, (cudaStream_t)stream>>>(corners, n, eps, flags);
     return check_launch("box3d_check_kernel");
+}
+
+extern "C" int pp_assign_overlaps(const float *gt, int64_t G, const float *anchors, int64_t A, int iou_mode, float lo_thr,
+                                  float *max_ov, int32_t *argmax, float *gt_max, uint8_t *lowq, pp_stream_t stream)
+{
+    pp::enter((cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    PP_REQUIRE(G >= 1 && G < (1 << 30) && A >= 0, "bad sizes (needs at least one ground truth)");
+    PP_REQUIRE(iou_mode == PP_NMS_AABB2D || iou_mode == PP_NMS_BOX3D, "iou_mode must be PP_NMS_AABB2D or PP_NMS_BOX3D");
+    PP_REQUIRE(gt && gt_max, "null pointer");
+    PP_CUDA_TRY(cudaMemsetAsync(gt_max, 0, (size_t)G * sizeof(float), st));
+    prof_mark("memset");
+    if (A == 0) return PP_OK;
+    PP_REQUIRE(anchors && max_ov && argmax && lowq, "null pointer");
+    PP_REQUIRE(iou_mode != PP_NMS_AABB2D || (((uintptr_t)gt | (uintptr_t)anchors) % 16 == 0), "rectangles must be 16-byte aligned");
+    const unsigned grid = (unsigned)ceil_div(A, AS_THREADS);
+    if (iou_mode == PP_NMS_AABB2D) {
+        assign_kernel<PP_NMS_AABB2D, false><<<grid, AS_THREADS, 0, st>>>(gt, (int)G, anchors, A, lo_thr, max_ov, argmax, gt_max, lowq);
+        if (int rc = check_launch("assign_kernel")) return rc;
+        assign_kernel<PP_NMS_AABB2D, true><<<grid, AS_THREADS, 0, st>>>(gt, (int)G, anchors, A, lo_thr, max_ov, argmax, gt_max, lowq);
+    } else {
+        assign_kernel<PP_NMS_BOX3D, false><<<grid, AS_THREADS, 0, st>>>(gt, (int)G, anchors, A, lo_thr, max_ov, argmax, gt_max, lowq);
+        if (int rc = check_launch("assign_kernel")) return rc;
+        assign_kernel<PP_NMS_BOX3D, true><<<grid, AS_THREADS, 0, st>>>(gt, (int)G, anchors, A, lo_thr, max_ov, argmax, gt_max, lowq);
+    }
+    return check_launch("assign_kernel");
 }

@@ -13,9 +13,10 @@ from torch import nn
 from torch.nn import functional as F
 
 from . import _lib
-from .model_utils import Anchor3DRangeGenerator, BBoxCoder, limit_period, multiclass_nms
+from .model_utils import Anchor3DRangeGenerator, BBoxCoder, assign_overlaps, limit_period, multiclass_nms
 from .ops_numba import VoxelGenerator, _ptr, _stream, voxel_cfg, voxelize_device
-from .ops_torch import bbox2corners3D, bbox2rotated_corners2D, bbox_iou2D, box3d_overlap
+from .ops_torch import (bbox2corners3D, bbox2rotated_corners2D, bbox_iou2D, box3d_overlap, check_coplanar,
+                        check_nonzero)
 
 
 class PointPillarsVoxelization(nn.Module):
@@ -290,11 +291,11 @@ class Anchor3DHead(nn.Module):
         anchors_cnt = int(np.prod(anchors.shape[:-1]))
         rot_angles = anchors.shape[-2]
         flat = anchors.reshape(-1, self.box_params_num)
-        if self.nms_dim == 3:
-            box2vertices, box_overlap = bbox2corners3D, box3d_overlap          # :899-901
-        else:
-            box2vertices, box_overlap = bbox2rotated_corners2D, bbox_iou2D     # :903-905
+        box2vertices = bbox2corners3D if self.nms_dim == 3 else bbox2rotated_corners2D      # :899-905
         anchor_rect = box2vertices(flat)
+        if self.nms_dim == 3:
+            check_coplanar(anchor_rect, 1e-2)
+            check_nonzero(anchor_rect, 1e-2)
         assigned, target_idxs, pos_idxs, neg_idxs = [], [], [], []
 
         def flatten_idx(idx, j):
@@ -309,14 +310,15 @@ class Anchor3DHead(nn.Module):
                     for lst in (target_idxs, pos_idxs, neg_idxs):
                         lst.append(torch.zeros((0,), dtype=torch.long, device=dev))
                     continue
-                overlaps = box_overlap(box2vertices(gts), anchor_rect)          # :964-965
-                max_ov, argmax_ov = overlaps.max(dim=0)
-                gt_max, _ = overlaps.max(dim=1)
                 lo, hi = self.iou_thr[j]
-                pos = max_ov >= hi
+                gt_vertices = box2vertices(gts)
+                if self.nms_dim == 3:                      # box3d_overlap's validity checks (ops_torch.py:743-748)
+                    check_coplanar(gt_vertices, 1e-2)
+                    check_nonzero(gt_vertices, 1e-2)
+                # IoU (:964-965) fused with both maxima (:968-971) and the low-quality matching (:976-978)
+                max_ov, argmax_ov, _, lowq = assign_overlaps(gt_vertices, anchor_rect, lo, self.nms_dim)
+                pos = (max_ov >= hi) | lowq
                 neg = (max_ov >= 0) & (max_ov < lo)
-                # low-quality matching (:976-978), vectorised over the ground truths
-                pos |= ((overlaps == gt_max[:, None]) & (gt_max >= lo)[:, None]).any(dim=0)
                 assigned.append(self.bbox_coder.encode(flat[pos], gts[argmax_ov[pos]]))
                 target_idxs.append(argmax_ov[pos] + idx_off)
                 pos_idxs.append(flatten_idx(pos.nonzero(as_tuple=False).squeeze(-1), j) + i * anchors_cnt)

