@@ -217,6 +217,24 @@ PP_API int pp_nms_mode(const float *boxes9, const float *scores, int64_t score_s
                 size_t workspace_bytes, pp_stream_t stream);
 
 /*
+ * Fused head post-processing, Anchor3DHead.get_bboxes_single, model/PointPillars.py:1040-1092.
+ * Head tensors stay in the conv layout (channels, H, W); row r = (y*W + x)*A + a of the reference's
+ * permute(1,2,0).reshape(-1, k) views reads channels a*k .. a*k+k-1 at (y, x); A = S*R anchors per position.
+ *  pp_head_max_scores     max_scores[r] = max_c sigmoid(cls[a*ncls + c, y, x])                         (:1050-1058)
+ *  pp_head_select_decode  for the K selected rows (rows == NULL: rows 0..K-1): anchor generated on the fly
+ *                         (model/utils.py:168-264, never materialised), boxes (K,9) = BBoxCoder.decode, scores (K,ncls)
+ *                         = sigmoid(logits), dir_bits (K,3) = argmax of the three direction logit pairs  (:1045-1065)
+ *  pp_head_direction_fixup  boxes[:, 6:9] = limit_period(rot - off, 1, pi) + off + pi * bit, in place    (:1085-1092)
+ * range6 / sizes (S,3) / rots (R,3) are HOST arrays like pp_grid_anchors'.
+ */
+PP_API int pp_head_max_scores(const float *cls, int anchors_per_pos, int ncls, int H, int W, float *max_scores,
+                       pp_stream_t stream);
+PP_API int pp_head_select_decode(const float *cls, const float *reg, const float *dirs, const int64_t *rows, int64_t K,
+                          const float *range6_host, const float *sizes_host, int S, const float *rots_host, int R,
+                          int ncls, int H, int W, float *boxes, float *scores, int32_t *dir_bits, pp_stream_t stream);
+PP_API int pp_head_direction_fixup(float *boxes, const int32_t *dir_bits, int64_t K, float dir_offset, pp_stream_t stream);
+
+/*
  * Target assignment reductions of Anchor3DHead.assign_bboxes, model/PointPillars.py:964-978, without the (G, A)
  * IoU matrix: for every anchor the best IoU over the ground truths and the FIRST ground truth reaching it (:968),
  * for every ground truth its best IoU over the anchors (:971), and the low-quality-match flag (:976-978):

@@ -61,6 +61,10 @@ SIGNATURES = {
     "pp_box3d_overlap": (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "pp_box3d_check": (ctypes.c_int, [_vp, _i64, _f32, _vp, _vp]),
     "pp_assign_overlaps": (ctypes.c_int, [_vp, _i64, _vp, _i64, ctypes.c_int, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "pp_head_max_scores": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    "pp_head_select_decode": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "pp_head_direction_fixup": (ctypes.c_int, [_vp, _vp, _i64, _f32, _vp]),
     "pp_iou_jit": (ctypes.c_int, [_vp, _i64, _vp, _i64, _f64, _vp, _vp]),
     "pp_nms_workspace_bytes": (_sz, [_i64]),
     "pp_nms": (ctypes.c_int, [_vp, _vp, _i64, _i64, _f32, _f32, _vp, _vp, _vp, _sz, _vp]),

@@ -64,22 +64,93 @@ struct AnchorSpec {
     int S, R, D, H, W;
 };
 
-__global__ void __launch_bounds__(BX_THREADS) grid_anchors_kernel(const AnchorSpec a, int64_t total, float *__restrict__ out)
+// anchor i of grid_anchors(...).reshape(-1, 9): i = (((z*H + y)*W + x)*S + s)*R + r
+__device__ __forceinline__ void anchor_at(const AnchorSpec &a, int64_t i, float o[9])
 {
-    int64_t i = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;   // one thread per anchor
-    if (i >= total) return;
     int r = (int)(i % a.R);
     int64_t t = i / a.R;
     int s = (int)(t % a.S); t /= a.S;
     int x = (int)(t % a.W); t /= a.W;
     int y = (int)(t % a.H);
     int z = (int)(t / a.H);
-    float *o = out + i * 9;
     o[0] = linspace_at(a.range[0], a.range[3], a.W, x);
     o[1] = linspace_at(a.range[1], a.range[4], a.H, y);
     o[2] = linspace_at(a.range[2], a.range[5], a.D, z);
     o[3] = a.sizes[s * 3]; o[4] = a.sizes[s * 3 + 1]; o[5] = a.sizes[s * 3 + 2];
     o[6] = a.rots[r * 3]; o[7] = a.rots[r * 3 + 1]; o[8] = a.rots[r * 3 + 2];
+}
+
+__device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// ---- fused head post-processing, Anchor3DHead.get_bboxes_single (model/PointPillars.py:1040-1092) -----------------
+// The reference materialises every anchor (69 MB at its 400 x 400 map), permutes the three head tensors, decodes all
+// anchors and only then keeps nms_pre of them.  Here: (1) one pass over the class logits gives the per-anchor score
+// (sigmoid + class max, :1050-1058) straight from the (channels, H, W) layout; (2) after the top-k, the nms_pre
+// survivors get their anchor generated on the fly, their deltas / logits / direction logits gathered from the head
+// tensors, and are decoded (decode is element-wise, so decode-after-select equals the reference's decode-all).
+__global__ void __launch_bounds__(BX_THREADS)
+head_max_scores_kernel(const float *__restrict__ cls, int A_per, int ncls, int64_t HW, float *__restrict__ max_scores)
+{
+    const int64_t pos = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;      // y * W + x: coalesced channel rows
+    if (pos >= HW) return;
+    for (int a = 0; a < A_per; ++a) {
+        float m = -1.f;
+        for (int c = 0; c < ncls; ++c) m = fmaxf(m, sigmoid_f32(cls[(int64_t)(a * ncls + c) * HW + pos]));
+        max_scores[pos * A_per + a] = m;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+head_select_decode_kernel(const float *__restrict__ cls, const float *__restrict__ reg, const float *__restrict__ dirs,
+                          const int64_t *__restrict__ rows, int64_t K, const AnchorSpec spec, int ncls,
+                          float *__restrict__ boxes, float *__restrict__ scores, int32_t *__restrict__ dir_bits)
+{
+    const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (j >= K) return;
+    const int64_t r = rows ? rows[j] : j;
+    const int A_per = spec.S * spec.R;
+    const int64_t HW = (int64_t)spec.H * spec.W;
+    const int64_t pos = r / A_per;
+    const int a = (int)(r - pos * A_per);
+    float an[9], t[9], o[9];
+    anchor_at(spec, r, an);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) t[k] = reg[(int64_t)(a * 9 + k) * HW + pos];
+    decode_one(an, t, o);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) boxes[j * 9 + k] = o[k];
+    for (int c = 0; c < ncls; ++c) scores[j * ncls + c] = sigmoid_f32(cls[(int64_t)(a * ncls + c) * HW + pos]);
+    // row r of dir_preds.permute(1, 2, 0).reshape(-1, 6) = channels 6a .. 6a+5 of the concatenated tensor (:1045-1048)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float d0 = dirs[(int64_t)(a * 6 + 2 * k) * HW + pos], d1 = dirs[(int64_t)(a * 6 + 2 * k + 1) * HW + pos];
+        dir_bits[j * 3 + k] = d1 > d0 ? 1 : 0;                  // torch.max(...)[1]: first maximum
+    }
+}
+
+// direction fix-up of the kept boxes, :1085-1092: rot = limit_period(rot - off, 1, pi) + off + pi * bit
+__global__ void __launch_bounds__(BX_THREADS)
+head_fixup_kernel(float *__restrict__ boxes, const int32_t *__restrict__ dir_bits, int64_t K, float dir_offset)
+{
+    const int64_t i = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;
+    if (i >= K * 3) return;
+    const int64_t j = i / 3;
+    const int k = (int)(i - j * 3);
+    const float period = 3.14159274101257324f;                  // float32(np.pi)
+    const float v = __fsub_rn(boxes[j * 9 + 6 + k], dir_offset);
+    const float lp = __fsub_rn(v, __fmul_rn(floorf(__fadd_rn(__fdiv_rn(v, period), 1.0f)), period));
+    boxes[j * 9 + 6 + k] = __fadd_rn(__fadd_rn(lp, dir_offset), __fmul_rn(period, (float)dir_bits[j * 3 + k]));
+}
+
+__global__ void __launch_bounds__(BX_THREADS) grid_anchors_kernel(const AnchorSpec a, int64_t total, float *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * BX_THREADS + threadIdx.x;   // one thread per anchor
+    if (i >= total) return;
+    float *o = out + i * 9;
+    float v[9];
+    anchor_at(a, i, v);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = v[k];
 }
 
 __global__ void __launch_bounds__(BX_THREADS)
@@ -491,4 +562,54 @@ extern "C" int pp_assign_overlaps(const float *gt, int64_t G, const float *ancho
         assign_kernel<PP_NMS_BOX3D, true><<<grid, AS_THREADS, 0, st>>>(gt, (int)G, anchors, A, lo_thr, max_ov, argmax, gt_max, lowq);
     }
     return check_launch("assign_kernel");
+}
+
+static int fill_anchor_spec(AnchorSpec &a, const float *range6_host, const float *sizes_host, int S, const float *rots_host,
+                            int R, int D, int H, int W)
+{
+    PP_REQUIRE(range6_host && sizes_host && rots_host, "null pointer");
+    PP_REQUIRE(S > 0 && S <= 16 && R > 0 && R <= 16, "1..16 sizes / rotations supported");
+    PP_REQUIRE(D > 0 && H > 0 && W > 0, "bad feature map");
+    for (int i = 0; i < 6; ++i) a.range[i] = range6_host[i];
+    for (int i = 0; i < S * 3; ++i) a.sizes[i] = sizes_host[i];
+    for (int i = 0; i < R * 3; ++i) a.rots[i] = rots_host[i];
+    a.S = S; a.R = R; a.D = D; a.H = H; a.W = W;
+    return PP_OK;
+}
+
+extern "C" int pp_head_max_scores(const float *cls, int anchors_per_pos, int ncls, int H, int W, float *max_scores,
+                                  pp_stream_t stream)
+{
+    pp::enter((cudaStream_t)stream);
+    PP_REQUIRE(cls && max_scores, "null pointer");
+    PP_REQUIRE(anchors_per_pos > 0 && ncls > 0 && H > 0 && W > 0, "bad shape");
+    const int64_t HW = (int64_t)H * W;
+    head_max_scores_kernel<<<GRID1(HW)>>>(cls, anchors_per_pos, ncls, HW, max_scores);
+    return check_launch("head_max_scores_kernel");
+}
+
+extern "C" int pp_head_select_decode(const float *cls, const float *reg, const float *dirs, const int64_t *rows, int64_t K,
+                                     const float *range6_host, const float *sizes_host, int S, const float *rots_host,
+                                     int R, int ncls, int H, int W, float *boxes, float *scores, int32_t *dir_bits,
+                                     pp_stream_t stream)
+{
+    pp::enter((cudaStream_t)stream);
+    PP_REQUIRE(K >= 0 && ncls > 0, "bad shape");
+    AnchorSpec a;
+    if (int rc = fill_anchor_spec(a, range6_host, sizes_host, S, rots_host, R, 1, H, W)) return rc;
+    if (K == 0) return PP_OK;
+    PP_REQUIRE(cls && reg && dirs && boxes && scores && dir_bits, "null pointer");
+    head_select_decode_kernel<<<(unsigned)ceil_div(K, 128), 128, 0, (cudaStream_t)stream>>>(cls, reg, dirs, rows, K, a, ncls,
+                                                                                          boxes, scores, dir_bits);
+    return check_launch("head_select_decode_kernel");
+}
+
+extern "C" int pp_head_direction_fixup(float *boxes, const int32_t *dir_bits, int64_t K, float dir_offset, pp_stream_t stream)
+{
+    pp::enter((cudaStream_t)stream);
+    PP_REQUIRE(K >= 0, "K < 0");
+    if (K == 0) return PP_OK;
+    PP_REQUIRE(boxes && dir_bits, "null pointer");
+    head_fixup_kernel<<<GRID1(K * 3)>>>(boxes, dir_bits, K, dir_offset);
+    return check_launch("head_fixup_kernel");
 }

@@ -255,6 +255,51 @@ class Anchor3DHead(nn.Module):
         return [o[0] for o in out], [o[1] for o in out], [o[2] for o in out]
 
     def get_bboxes_single(self, cls_scores, bbox_preds, dir_preds):
+        """:1025-1094 on the fused kernels: per-anchor score straight from the conv layout, top-k, then anchors
+        generated on the fly + gather + decode for the nms_pre survivors only, NMS, fused direction fix-up."""
+        assert cls_scores.size()[-2:] == bbox_preds.size()[-2:]
+        assert cls_scores.size()[-2:] == dir_preds.size()[-2:]
+        lib = _lib.load()
+        H, W = (int(v) for v in cls_scores.shape[-2:])
+        A, ncls = self.num_anchors, self.num_classes
+        dev = cls_scores.device
+        cls = cls_scores.detach().to(torch.float32).contiguous()
+        reg = bbox_preds.detach().to(torch.float32).contiguous()
+        dirs = dir_preds.detach().to(torch.float32).contiguous()
+        assert cls.shape[0] == A * ncls and reg.shape[0] == A * self.box_params_num and dirs.shape[0] == A * 6
+        total = H * W * A
+        rows, K = None, total
+        if total > self.nms_pre:
+            max_scores = torch.empty((total,), dtype=torch.float32, device=dev)
+            _lib.check(lib.pp_head_max_scores(_ptr(cls), A, ncls, H, W, _ptr(max_scores), _stream()))
+            _, rows = max_scores.topk(self.nms_pre)                      # :1058-1059
+            rows, K = rows.contiguous(), self.nms_pre
+        gen = self.anchor_generator
+        assert len(gen.ranges) == 1, "one anchor range (as in config.yaml:64)"
+        fp = ctypes.POINTER(ctypes.c_float)
+        rg = np.asarray(gen.ranges[0], dtype=np.float32)
+        sizes = np.ascontiguousarray(np.asarray(gen.sizes, dtype=np.float32).reshape(-1, 3))
+        rots = np.ascontiguousarray(np.asarray(gen.rotations, dtype=np.float32).reshape(-1, 3))
+        bboxes = torch.empty((K, 9), dtype=torch.float32, device=dev)
+        scores = torch.empty((K, ncls), dtype=torch.float32, device=dev)
+        dir_bits = torch.empty((K, 3), dtype=torch.int32, device=dev)
+        _lib.check(lib.pp_head_select_decode(_ptr(cls), _ptr(reg), _ptr(dirs), _ptr(rows) if rows is not None else None, K,
+                                             rg.ctypes.data_as(fp), sizes.ctypes.data_as(fp), sizes.shape[0],
+                                             rots.ctypes.data_as(fp), rots.shape[0], ncls, H, W, _ptr(bboxes), _ptr(scores),
+                                             _ptr(dir_bits), _stream()))
+        idxs = multiclass_nms(bboxes, scores, self.score_thr, self.nms_thresh, self.nms_dim)
+        labels = torch.cat([torch.full((len(idxs[i]),), i, dtype=torch.long) for i in range(ncls)])
+        out_scores = torch.cat([scores[idxs[i], i] for i in range(ncls)])
+        idxs = torch.cat(idxs)
+        bboxes = bboxes[idxs].contiguous()
+        dir_bits = dir_bits[idxs].contiguous()
+        _lib.check(lib.pp_head_direction_fixup(_ptr(bboxes), _ptr(dir_bits), bboxes.shape[0], float(self.dir_offset),
+                                               _stream()))
+        return bboxes, out_scores, labels
+
+    def get_bboxes_single_unfused(self, cls_scores, bbox_preds, dir_preds):
+        """The same function in the reference's own order of operations (materialised anchors, permuted views,
+        per-op kernels): kept as the in-repo cross-check of the fused path (tests/test_gpu_parity.py)."""
         assert cls_scores.size()[-2:] == bbox_preds.size()[-2:]
         assert cls_scores.size()[-2:] == dir_preds.size()[-2:]
         anchors = self.anchor_generator.grid_anchors(cls_scores.shape[-2:], device=cls_scores.device)

@@ -265,6 +265,18 @@ def test_head_golden(pp):
     assert_close_t1(s.cpu().numpy(), g["scores"], what="scores")
     assert_close_t1(b.cpu().numpy(), g["bboxes"], atol=1e-5, what="bboxes")
     assert np.array_equal(l.numpy(), g["labels"])
+    with torch.no_grad():           # the fused path against the reference's order of operations on the same GPU
+        b2, s2, l2 = head.get_bboxes_single_unfused(cu(g["cls"]), cu(g["reg"]), cu(g["dirs"]))
+    assert torch.equal(l, l2) and b.shape == b2.shape
+    assert_close_t1(s.cpu().numpy(), s2.cpu().numpy(), atol=1e-6, what="fused vs unfused scores")
+    assert_close_t1(b.cpu().numpy(), b2.cpu().numpy(), atol=1e-5, what="fused vs unfused boxes")
+    head.nms_pre = 10 ** 9          # no top-k: every anchor goes through select/decode (rows == NULL)
+    with torch.no_grad():
+        b3, s3, l3 = head.get_bboxes_single(cu(g["cls"]), cu(g["reg"]), cu(g["dirs"]))
+        b4, s4, l4 = head.get_bboxes_single_unfused(cu(g["cls"]), cu(g["reg"]), cu(g["dirs"]))
+    assert torch.equal(l3, l4) and b3.shape == b4.shape and len(b3) >= len(b)
+    assert_close_t1(b3.cpu().numpy(), b4.cpu().numpy(), atol=1e-5, what="fused vs unfused boxes (no top-k)")
+    head.nms_pre = 300
     with torch.no_grad():
         ab, ti, pi, ni = head.assign_bboxes(cu(g["reg"]).unsqueeze(0), [cu(g["gts"])])
     assert np.array_equal(ti.cpu().numpy(), g["target_idx"])
