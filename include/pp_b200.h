@@ -245,6 +245,28 @@ PP_API int pp_head_direction_fixup(float *boxes, const int32_t *dir_bits, int64_
 PP_API int pp_assign_overlaps(const float *gt, int64_t G, const float *anchors, int64_t A, int iou_mode, float lo_thr,
                        float *max_ov, int32_t *argmax, float *gt_max, uint8_t *lowq, pp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Either side of the path.  Workspace for the three compacting calls:
+ * pp_compact_workspace_bytes(number of points / of canvas cells).
+ * ---------------------------------------------------------------------------------------- */
+PP_API size_t pp_compact_workspace_bytes(int64_t n);
+/* PointPillars.preprocess, model/PointPillars.py:241-266: optional global_outlier_check (ops/ops_numpy.py:111-115:
+ * keep |p - mean| < mean(norm) + 5 std(norm)), range filter lo <= xyz < hi (:251-252), feature selection (:266).
+ * out (n, n_features) holds *out_count rows in the input order.  range6 and features are HOST arrays. */
+PP_API int pp_preprocess_points(const float *points, int64_t n, int C, int outlier_check, const float *range6_host,
+                         const int32_t *features_host, int n_features, float *out, int32_t *out_count,
+                         void *workspace, size_t workspace_bytes, pp_stream_t stream);
+/* min / max of xyz -> out6 (device): the point_cloud_range of CustomVoxelizer.voxelize, model/utils.py:17-18 */
+PP_API int pp_points_minmax(const float *points, int64_t n, int C, float *out6, void *workspace, size_t workspace_bytes,
+                     pp_stream_t stream);
+/* np.sum(vox, axis=1) / vp with vp appended, model/utils.py:34-43: (M,P,C),(M) -> (M, C+1) */
+PP_API int pp_voxel_centroids(const float *voxels, const int32_t *num_points, int64_t M, int P, int C, float *out,
+                       pp_stream_t stream);
+/* SubmanifoldSparseRPN.forward's dense -> sparse step, model/PointPillars.py:766-789: cells of x (B,C,H,W) with any
+ * non-zero channel in (b, y, x) row-major order -> coords (nnz,3) int32, values (nnz,C); *nnz device scalar. */
+PP_API int pp_dense_to_sparse(const float *x, int B, int C, int H, int W, int32_t *coords, float *values, int32_t *nnz,
+                       void *workspace, size_t workspace_bytes, pp_stream_t stream);
+
 /* Stable radix sort of (u32 key, u32 value) pairs, ascending; building block exposed for tests. */
 PP_API size_t pp_sort_workspace_bytes(int64_t n);
 PP_API int pp_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out,

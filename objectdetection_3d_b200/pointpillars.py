@@ -210,6 +210,25 @@ class SparseMiddleExtractor(nn.Module):
         return _DenseScatter.apply(voxel_features, coors, int(batch_size), D, H, W)
 
 
+def dense_to_sparse(x):
+    """The dense -> sparse step of SubmanifoldSparseRPN.forward, model/PointPillars.py:766-789: the cells of x
+    (B,C,H,W) with any non-zero channel, in (b, y, x) row-major order.  Returns (values (nnz,C) f32, coords (nnz,3)
+    int32 = [b, y, x]), i.e. the arguments of spconv.SparseConvTensor(values, coords, x.shape[-2:], x.shape[0])."""
+    lib = _lib.load()
+    x = x.detach().float().contiguous()
+    B, C, H, W = (int(v) for v in x.shape)
+    cells = B * H * W
+    coords = torch.empty((cells, 3), dtype=torch.int32, device=x.device)
+    values = torch.empty((cells, C), dtype=torch.float32, device=x.device)
+    nnz = torch.zeros((1,), dtype=torch.int32, device=x.device)
+    ws_bytes = int(lib.pp_compact_workspace_bytes(cells))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.pp_dense_to_sparse(_ptr(x), B, C, H, W, _ptr(coords), _ptr(values), _ptr(nnz), _ptr(ws), ws_bytes,
+                                      _stream()))
+    k = int(nnz.item())
+    return values[:k], coords[:k]
+
+
 class Anchor3DHead(nn.Module):
     """model/PointPillars.py:795-1094.  The 1x1 conv heads are stock torch; get_bboxes / assign_bboxes
     run the box decode, BEV IoU, NMS and encode kernels of libpp_b200 (nms_dim == 2 form)."""

@@ -281,3 +281,56 @@ def assign_overlaps(overlaps, lo_thr):
     gt_max = ov.max(axis=1)
     lowq = ((ov == gt_max[:, None]) & (gt_max >= ov.dtype.type(lo_thr))[:, None]).any(axis=0)
     return ov.max(axis=0), ov.argmax(axis=0), gt_max, lowq
+
+
+# ---- either side of the path -------------------------------------------------------------------------
+def global_outlier_check(point_cloud):
+    """ops/ops_numpy.py:111-115, restated op for op in numpy (the reference is numpy)."""
+    norm = np.sum((point_cloud[:, :3] - np.mean(point_cloud[:, :3], axis=0)) ** 2, axis=1) ** 0.5
+    return point_cloud[norm < np.mean(norm) + 5 * np.std(norm), :]
+
+
+def preprocess_points(points, point_cloud_range, input_features, outlier=True):
+    """model/PointPillars.py:241-266 without the bbox filter and the augmentation: outlier check, range filter,
+    feature selection."""
+    if outlier:
+        points = global_outlier_check(points)
+    points = np.array(points, dtype=np.float32)
+    lo, hi = np.array(point_cloud_range[:3]), np.array(point_cloud_range[3:])
+    points = points[np.where(np.all(np.logical_and(points[:, :3] >= lo, points[:, :3] < hi), axis=-1))]
+    return points[:, input_features]
+
+
+def custom_voxelizer_voxelize(point_cloud, voxel_size, max_voxel_points, reflectance_sampling, perm=None):
+    """model/utils.py:15-43 (CustomVoxelizer.voxelize) on the oracle voxelizer: the cloud's own min/max as a Python list
+    (-> all-f32 cell arithmetic), density-dependent pillar cap, centroids with the point count appended.
+    Raises UnboundLocalError like the reference when neither branch voxelizes (:43 reads an unbound `vp`)."""
+    rng = point_cloud[:, :3].min(axis=0).tolist() + point_cloud[:, :3].max(axis=0).tolist()
+    dims = point_cloud[:, :3].max(axis=0) - point_cloud[:, :3].min(axis=0)
+    density = point_cloud.shape[0] / np.prod(dims)
+    a, b, c, voxel_limit = 20000, 0.01, 70000, 3000000
+    vp = None
+    if density > 10:
+        max_voxels = np.min([int(a * np.exp(b * density) + c), point_cloud.shape[0]])
+        if max_voxels <= point_cloud.shape[0]:
+            max_voxels = np.min([max_voxels, voxel_limit])
+            vox, _, vp = points_to_voxel(point_cloud, np.array(voxel_size, dtype=np.float32), rng, max_voxel_points,
+                                         int(max_voxels), reflectance_sampling, perm=perm)
+            point_cloud = np.sum(vox, axis=1) / vp.reshape(-1, 1)
+    elif point_cloud.shape[0] > voxel_limit:
+        vox, _, vp = points_to_voxel(point_cloud, np.array(voxel_size, dtype=np.float32), rng, max_voxel_points,
+                                     voxel_limit, reflectance_sampling, perm=perm)
+        point_cloud = np.sum(vox, axis=1) / vp.reshape(-1, 1)
+    if vp is None:
+        raise UnboundLocalError("cannot access local variable 'vp' where it is not associated with a value")
+    return np.concatenate((point_cloud, vp.reshape(-1, 1)), axis=1)
+
+
+def dense_to_sparse(x):
+    """model/PointPillars.py:766-789: non-empty cells of a dense (B,C,H,W) map in row-major order."""
+    coords, values = [], []
+    for i in range(x.shape[0]):
+        ys, xs = np.where((x[i] != 0).any(axis=0))
+        coords.append(np.stack([np.full_like(ys, i), ys, xs], axis=1).astype(np.int32))
+        values.append(x[i][:, ys, xs].T)
+    return np.concatenate(values, axis=0), np.concatenate(coords, axis=0)

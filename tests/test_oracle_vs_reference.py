@@ -47,3 +47,25 @@ def test_nms_live(oracle, R):
         got = oracle.multiclass_nms(boxes, scores, 0.2, ithr, 2)[0]
         assert set(ref.tolist()) == set(got.tolist())
         assert (np.diff(scores[got, 0]) < 0).all()
+
+
+def test_outlier_check_and_custom_voxelizer_live(oracle, R):
+    """the numpy restatements against the reference's own functions."""
+    import importlib
+    from objectdetection_3d_b200 import synth
+    ops_numpy = importlib.import_module("ops.ops_numpy")
+    pts = synth.forest_tile(n=40_000, seed=31)
+    pts[::997, :3] += 400.0                                             # outliers
+    assert np.array_equal(oracle.global_outlier_check(pts), ops_numpy.global_outlier_check(pts))
+    # CustomVoxelizer: a dense cloud (density > 10 points / m^3) so that the downsample branch runs
+    rng = np.random.default_rng(32)
+    cloud = np.concatenate([rng.uniform(0, 6, (60_000, 3)), rng.permutation(60_000)[:, None] / 60_000.0], axis=1).astype(np.float32)
+    cfg = dict(voxel_size=[0.25, 0.25, 0.25], max_voxel_points=8, reflectance_sampling=True)
+    ref = R.utils.CustomVoxelizer(cfg).voxelize(cloud.copy())
+    got = oracle.custom_voxelizer_voxelize(cloud, cfg["voxel_size"], 8, True)
+    assert ref.shape == got.shape and ref.shape[1] == 5 and ref.shape[0] < cloud.shape[0]
+    assert np.array_equal(ref[:, 4], got[:, 4]) and np.allclose(ref, got, rtol=1e-6, atol=1e-6)
+    with pytest.raises(UnboundLocalError):
+        R.utils.CustomVoxelizer(cfg).voxelize(cloud[:50].copy() * 100)   # sparse cloud: the reference's unbound `vp`
+    with pytest.raises(UnboundLocalError):
+        oracle.custom_voxelizer_voxelize(cloud[:50] * 100, cfg["voxel_size"], 8, True)
