@@ -364,6 +364,23 @@ def run_ours(args):
 
     t_vox, t_enc, t_nms = split_pass(min(K, 50))
 
+    # ---- the other pair tests of the NMS on the same 20k boxes (not part of the step) ------------
+    def nms_mode_us(mode, reps=30):
+        st_ = pipeline.NmsStage(N_BOXES, device=dev, iou_mode=mode)
+        for _ in range(3):
+            st_.run(d_boxes[0], d_scores[0], NMS_SCORE_THR, NMS_IOU_THR, 0, stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for r in range(reps):
+            st_.run(d_boxes[r % RING_TILES], d_scores[r % RING_TILES], NMS_SCORE_THR, NMS_IOU_THR, 0, stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return 1e3 * e0.elapsed_time(e1) / reps, int(st_.count.item())
+
+    t_rot, kept_rot = nms_mode_us(_lib.NMS_ROT_BEV)
+    t_b3d, kept_b3d = nms_mode_us(_lib.NMS_BOX3D)
+
     # ---- per-kernel durations with CUDA events on the launching stream (library profiler) --------
     _lib.profile(True)
     prof_steps = min(K, 50)
@@ -405,6 +422,7 @@ def run_ours(args):
     kbytes = {"scatter_canvas_kernel": canvas_b + m_pillars * (pipe.U + 1) * 4,
               "vox_scatter_kernel": N_POINTS * pipe.C * 4,
               "vox_gather_kernel": m_pillars * pipe.P * pipe.C * 4 + m_pillars * 4,
+              "vox_gather_sorted_kernel": m_pillars * pipe.P * pipe.C * 4 + m_pillars * 4,
               "pfn_fused_small_kernel": m_pillars * pipe.P * pipe.C * 4 + m_pillars * 16 + m_pillars * (pipe.U + 1) * 4}
     # the roofline object is for the dominant kernel of the voxelize+scatter path (the HBM-bound stages of the
     # north star); the NMS kernels are ALU / latency bound and are listed with their times under "kernels"
@@ -430,7 +448,12 @@ def run_ours(args):
         "voxelize+scatter": {"algorithmic_MB": (vox_b + enc_b) / 1e6, "us": 1e3 * (t_vox + t_enc),
                              "frac": (vox_b + enc_b) / ((t_vox + t_enc) * 1e-3) / 1e9 / hbm_peak,
                              "target_frac": 0.6},
-        "nms_20k": {"us": 1e3 * t_nms, "target_us": 1000.0, "kept": keep_n}}
+        "nms_20k": {"us": 1e3 * t_nms, "target_us": 1000.0, "kept": keep_n,
+                    "pair_test": "xy rectangle of the rotated box (the reference's nms_dim == 2)"},
+        "nms_20k_rotated_bev": {"us": t_rot, "target_us": 1000.0, "kept": kept_rot,
+                                "pair_test": "rotated BEV polygon clipping (north-star extension)"},
+        "nms_20k_box3d": {"us": t_b3d, "kept": kept_b3d,
+                          "pair_test": "oriented 3-D box IoU (the reference's nms_dim == 3, config.yaml:6)"}}
     cpu = cpu_baseline(args.cpu_seconds) if world == 1 else None
     line = {"metric": "voxelize+scatter+NMS frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",

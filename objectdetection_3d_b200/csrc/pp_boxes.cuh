@@ -366,6 +366,35 @@ __device__ __forceinline__ float box3_inter_volume(const Box3 &a, const Box3 &b,
     return fminf(v, fminf(va, vb));
 }
 
+// Image of a in b's unit frame, axis by axis: false when an axis of b separates the boxes; else ub = vol(b) x the
+// product of the overlap lengths, an upper bound of the intersection volume (the intersection lies inside b and
+// inside the b-aligned bounding box of a).
+__device__ __forceinline__ bool box3_proj_bound(const Box3 &a, const Box3 &b, float &ub)
+{
+    const float d2 = det3(b.e[0], b.e[1], b.e[2]);
+    if (d2 == 0.f) { ub = 0.f; return false; }
+    float g2[3][3];
+    dual3(b.e, d2, g2);
+    const float dx = a.o[0] - b.o[0], dy = a.o[1] - b.o[1], dz = a.o[2] - b.o[2];
+    float prod = fabsf(d2);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float po = g2[r][0] * dx + g2[r][1] * dy + g2[r][2] * dz;
+        float lo = po, hi = po;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float pe = g2[r][0] * a.e[k][0] + g2[r][1] * a.e[k][1] + g2[r][2] * a.e[k][2];
+            lo += fminf(pe, 0.f);
+            hi += fmaxf(pe, 0.f);
+        }
+        const float len = fminf(hi, 1.f) - fmaxf(lo, 0.f);
+        if (!(len > 0.f)) { ub = 0.f; return false; }
+        prod *= len;
+    }
+    ub = prod;
+    return true;
+}
+
 // Symmetric by construction (canonical argument order), like rrect_iou.
 __device__ __forceinline__ float box3_iou(const Box3 &a, const Box3 &b, float *vol_out)
 {

@@ -32,6 +32,7 @@ template <> struct PairGeom<PP_NMS_AABB2D> {
     struct T {};
     static __device__ __forceinline__ T load(const float4 *, const float4 *, const float4 *, int) { return T(); }
     static __device__ __forceinline__ float iou(const T &, const T &) { return 0.f; }
+    static __device__ __forceinline__ bool exceeds(const T &, const T &, float) { return false; }
 };
 template <> struct PairGeom<PP_NMS_ROT_BEV> {
     typedef RRect T;
@@ -41,6 +42,7 @@ template <> struct PairGeom<PP_NMS_ROT_BEV> {
         return rrect_pack(a0[i], make_float2(h.x, h.y));
     }
     static __device__ __forceinline__ float iou(const T &a, const T &b) { return rrect_iou(a, b); }
+    static __device__ __forceinline__ bool exceeds(const T &a, const T &b, float thr) { return rrect_iou(a, b) > thr; }
 };
 template <> struct PairGeom<PP_NMS_BOX3D> {
     typedef Box3 T;
@@ -49,6 +51,23 @@ template <> struct PairGeom<PP_NMS_BOX3D> {
         return box3_load(a0[i], a1[i], a2[i]);
     }
     static __device__ __forceinline__ float iou(const T &a, const T &b) { return box3_iou(a, b, nullptr); }
+    // iou > thr?  Most pairs are decided without clipping: an axis of either box separates them, or the intersection,
+    // which lies inside box b and inside the b-aligned bounding box of a (and vice versa), is too small to reach the
+    // threshold (iou is increasing in the volume; the bound is inflated by 1e-3 relative, far above the fp32 error of
+    // the clipped volume).
+    static __device__ __forceinline__ bool exceeds(const T &a, const T &b, float thr)
+    {
+        if (thr >= 0.f) {
+            // separating axes of either box: no intersection (box3_iou returns 0 for these, and 0 > thr is false)
+            float ub1, ub2;
+            if (!box3_proj_bound(a, b, ub1) || !box3_proj_bound(b, a, ub2)) return false;
+            const float ub = fminf(ub1, ub2) * 1.001f;
+            const float va = fabsf(det3(a.e[0], a.e[1], a.e[2])), vb = fabsf(det3(b.e[0], b.e[1], b.e[2]));
+            // iou(ub) = ub / (va + vb - ub) <= thr  <=>  ub * (1 + thr) <= thr * (va + vb)
+            if (ub * (1.f + thr) <= thr * (va + vb)) return false;
+        }
+        return box3_iou(a, b, nullptr) > thr;
+    }
 };
 
 __global__ void __launch_bounds__(NMS_THREADS)
@@ -202,10 +221,10 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
             if (MODE != PP_NMS_AABB2D) {
                 // same definition as pp_iou_rotated_bev / pp_box3d_overlap: 0 unless the fp32 xy bounding rectangles
                 // overlap, else the clipped-polygon (polyhedron) IoU, symmetric in its arguments
-                float v = 0.f;
                 if (fminf(a.z, q.z) > fmaxf(a.x, q.x) && fminf(a.w, q.w) > fmaxf(a.y, q.y))
-                    v = G::iou(G::load(s_a0, s_a1, s_a2, wd * 64 + j), ga);
-                hit = v > thr;
+                    hit = G::exceeds(G::load(s_a0, s_a1, s_a2, wd * 64 + j), ga, thr);
+                else
+                    hit = 0.f > thr;
             } else if (PREFILTER) {
                 // iou > thr  <=>  overlap > thr * union, decided without the division unless the two sides are
                 // within 1e-6 relative of each other (then the reference's exact IEEE quotient is evaluated)
@@ -459,7 +478,7 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
                 const bool apart = !(fminf(box.z, q.z) > fmaxf(box.x, q.x) && fminf(box.w, q.w) > fmaxf(box.y, q.y));
                 bool hit;
                 if (apart) hit = zero_hits;
-                else if (MODE != PP_NMS_AABB2D) hit = G::iou(gbox, G::load(s_k0, s_k1, s_k2, j)) > thr;
+                else if (MODE != PP_NMS_AABB2D) hit = G::exceeds(gbox, G::load(s_k0, s_k1, s_k2, j), thr);
                 else hit = rect_iou(box, q, 0, 1e-6f) > thr;
                 if (hit) { dead = true; break; }
             }

@@ -24,7 +24,6 @@
 //   D  vox_gather*_kernel     per pillar: sort the row, drop keys >= cutoff, voxels[m][s] = points[row[s]]
 // Everything but the 16 B/point read and the output write is L2-resident workspace traffic.
 #include <math_constants.h>
-#include <stdlib.h>
 
 #include "pp_common.cuh"
 
@@ -825,8 +824,6 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
     init_blocks = init_blocks < 1 ? 1 : (init_blocks > 148 * 2 ? 148 * 2 : init_blocks);
     launch_pdl(vox_init_kernel, dim3(init_blocks + (WIDE ? 1 : 0)), dim3(1024), 0, st, points, n, prm.C, WIDE ? 1 : 0, w.coarse, w.fine, cv.ia);
     if (int rc = check_launch("vox_init_kernel")) return rc;
-    static const int stop_after = getenv("PP_VOX_STOP_AFTER") ? atoi(getenv("PP_VOX_STOP_AFTER")) : 99;
-    if (stop_after <= 1) return PP_OK;
     // persistent grid: exactly the CTAs that are resident at once (no partial last wave)
     static int sc_resident = 0;
     if (!sc_resident) {
@@ -834,26 +831,22 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
         PP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vox_scatter_kernel<K>, VOX_THREADS, 0));
         PP_CUDA_TRY(cudaGetDevice(&dev));
         PP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        if (getenv("PP_SCATTER_PER_SM")) per_sm = atoi(getenv("PP_SCATTER_PER_SM"));
         sc_resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
     }
     const int64_t sc_blocks = ceil_div(n, VOX_THREADS * SC_IT);
     launch_pdl(vox_scatter_kernel<K>, dim3((unsigned)(sc_blocks < sc_resident ? sc_blocks : sc_resident)), dim3(VOX_THREADS), 0, st,
                points, n, prm, perm, w);
     if (int rc = check_launch("vox_scatter_kernel")) return rc;
-    if (stop_after <= 2) return PP_OK;
     const unsigned cap = 148 * 8;    // persistent-style grids: the cell count is only known on the device
     auto capped = [&](int64_t blocks) { return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap); };
     launch_pdl(vox_cell_prefix_kernel<K>, dim3(capped(ceil_div(cv.Q, Q1_THREADS / 32)) / 4 + 1), dim3(Q1_THREADS), 0, st, prm, w);
     if (int rc = check_launch("vox_cell_prefix_kernel")) return rc;
-    if (stop_after <= 3) return PP_OK;
-    static const int place_per_sm = getenv("PP_PLACE_PER_SM") ? atoi(getenv("PP_PLACE_PER_SM")) : 4;
+    const int place_per_sm = 4;
     {
         const int64_t want = ceil_div(n, PLACE_THREADS * 4), cap_p = 148 * place_per_sm;
         launch_pdl(vox_place_kernel<K>, dim3((unsigned)(want < cap_p ? want : cap_p)), dim3(PLACE_THREADS), 0, st, n, prm, w);
     }
     if (int rc = check_launch("vox_place_kernel")) return rc;
-    if (stop_after <= 4) return PP_OK;
     {
         // cooperative: the CTAs meet at two grid barriers, so they must all be resident
         int64_t rb = ceil_div(cv.Q, RANK_THREADS);
@@ -880,7 +873,6 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
         PP_CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void *)vox_rank_kernel<K>, args));
         if (int rc = check_launch("vox_rank_kernel")) return rc;
     }
-    if (stop_after <= 5) return PP_OK;
     const bool vec4 = prm.vec4 && ((uintptr_t)voxels % 16 == 0);
     if (prm.ticket) {
         const unsigned gs = (unsigned)(ceil_div(max_rows, VOX_THREADS / 32) < 148 * 8 ? ceil_div(max_rows, VOX_THREADS / 32) : 148 * 8);

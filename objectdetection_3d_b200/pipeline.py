@@ -88,19 +88,20 @@ class FramePipeline:
 class NmsStage:
     """One class of multiclass_nms with preallocated buffers: boxes (N,9), scores (N,ncls) on device."""
 
-    def __init__(self, n_boxes, device=None):
+    def __init__(self, n_boxes, device=None, iou_mode=_lib.NMS_AABB2D):
         self.lib = _lib.load()
+        self.iou_mode = int(iou_mode)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n = int(n_boxes)
         self.keep = torch.empty((max(self.n, 1),), dtype=torch.int64, device=self.device)
         self.count = torch.zeros((1,), dtype=torch.int32, device=self.device)
-        self.ws_bytes = int(self.lib.pp_nms_workspace_bytes(self.n))
+        self.ws_bytes = int(self.lib.pp_nms_workspace_bytes_mode(self.n, self.iou_mode))
         self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=self.device)
 
     def run(self, boxes, scores, score_thr, iou_thr, cls_index=0, stream=None):
         stream = stream or torch.cuda.current_stream()
         sc = ctypes.c_void_p(scores.data_ptr() + 4 * cls_index)
-        _lib.check(self.lib.pp_nms(_ptr(boxes), sc, scores.shape[1], boxes.shape[0], float(np.float32(score_thr)),
-                                   float(np.float32(iou_thr)), _ptr(self.keep), _ptr(self.count), _ptr(self.ws),
-                                   self.ws_bytes, _sp(stream)))
+        _lib.check(self.lib.pp_nms_mode(_ptr(boxes), sc, scores.shape[1], boxes.shape[0], float(np.float32(score_thr)),
+                                        float(np.float32(iou_thr)), self.iou_mode, _ptr(self.keep), _ptr(self.count),
+                                        _ptr(self.ws), self.ws_bytes, _sp(stream)))
         return self.keep, self.count
