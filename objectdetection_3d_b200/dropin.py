@@ -9,13 +9,15 @@ model/PointPillars.py:899-905), so both the defining modules and the importing m
 """
 import importlib
 
-from . import model_utils, ops_numba, ops_torch, pointpillars
+from . import model_utils, ops_numba, ops_numpy, ops_torch, pointpillars
 
 PATCHES = {
     "ops.ops_numba": (ops_numba, ["points_to_voxel", "VoxelGenerator", "CustomVoxelGenerator", "iou_jit"]),
-    "ops.ops_torch": (ops_torch, ["bbox2rotated_corners2D", "bbox2corners3D", "bbox_iou2D"]),
+    "ops.ops_torch": (ops_torch, ["bbox2rotated_corners2D", "bbox2corners3D", "bbox_iou2D", "box3d_overlap",
+                                  "check_coplanar", "check_nonzero"]),
+    "ops.ops_numpy": (ops_numpy, ["global_outlier_check"]),
     "model.utils": (model_utils, ["Anchor3DRangeGenerator", "BBoxCoder", "limit_period", "multiclass_nms",
-                                  "get_paddings_indicator"]),
+                                  "get_paddings_indicator", "CustomVoxelizer"]),
     "model.PointPillars": (pointpillars, ["PointPillarsVoxelization", "PFNLayer", "PillarFeatureNet", "Anchor3DHead"]),
 }
 # names model/PointPillars.py imported from the modules above
