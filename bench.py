@@ -29,8 +29,8 @@ N_BOXES = 20_000
 NMS_SCORE_THR = 0.0      # every one of the 20k boxes is a candidate (scores are (perm + 0.5) / N > 0)
 NMS_IOU_THR = 0.1
 NMS_EXTENT = 40.0        # dense case of SURVEY.md 8(d) NMS20k
-RING_TILES = 12          # distinct input tiles per GPU  (12 x 16 MB), one per frame slot
-RING_CANVAS = 12         # distinct output canvases      (12 x 54.9 MB) -> working set > 126 MB L2
+RING_TILES = 24          # distinct input tiles per GPU  (24 x 16 MB), one per frame slot
+RING_CANVAS = 24         # distinct output canvases      (12 x 54.9 MB) -> working set > 126 MB L2
 WORKLOAD = "D1M tile (1e6 pts, 0.16 m pillars, 12000x32, 432x496 canvas, reflectance order) + NMS20k dense"
 
 
@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--slots", type=int, default=RING_TILES, help="frames in flight per GPU (<= %d)" % RING_TILES)
     return ap.parse_args()
 
 
@@ -251,7 +252,7 @@ def run_ours(args):
     # pipeline buffers: the single-CTA NMS sweep of one frame overlaps the grid-filling kernels of the others,
     # and (e2e) the H2D copy of frame i+1 overlaps the kernels of frame i.  A slot is reused only after its
     # stream has been synchronised, i.e. after that frame's results are complete (e2e: on the host).
-    N_SLOTS = RING_TILES
+    N_SLOTS = max(1, min(args.slots, RING_TILES))
     slots = []
     for k in range(N_SLOTS):
         sl = {"stream": torch.cuda.Stream(device=dev),

@@ -167,19 +167,8 @@ pfn_kernel(const PillarIn a, const float *__restrict__ W, const float *__restric
 
 // Fast path of the fused single-layer PillarFeatureNet (Cin <= 12, U <= 64): the two weight rows a lane owns live
 // in registers for the whole grid-stride loop, the decorated row is read back as broadcast 128-bit shared loads.
-// Dot products use packed FMAs (fma.rn.f32x2, two features per instruction; T1 against the reference's sgemm, the
-// decoration stays bit-exact).
+// Dot products use FMAs (T1 against the reference's sgemm; pp_decorate's decoration stays bit-exact).
 constexpr int PFN_LDI = 12;
-
-__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c)
-{
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;"
-        : "=l"(d)
-        : "l"(*reinterpret_cast<const unsigned long long *>(&a)), "l"(*reinterpret_cast<const unsigned long long *>(&b)),
-          "l"(*reinterpret_cast<const unsigned long long *>(&c)));
-    return *reinterpret_cast<float2 *>(&d);
-}
 
 // P <= 32: lane = slot while decorating (the pillar's points never leave registers until the decorated row is
 // staged for the broadcast reads), lane = channel pair while multiplying.  The mean is a shuffle tree here (T1; the
@@ -194,16 +183,13 @@ pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const floa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int P = a.P, C = a.C;
     constexpr int Cin = CIN;
-    constexpr int NP = (CIN + 1) / 2;          // feature pairs (the row is zero padded to PFN_LDI)
     float *row = smem + warp * 32 * PFN_LDI;
-    float2 w0[NP], w1[NP];
+    float w0[CIN], w1[CIN];
     const int u0 = lane, u1 = lane + 32;
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
-        w0[k].x = (u0 < U && 2 * k < Cin) ? W[u0 * Cin + 2 * k] : 0.f;
-        w0[k].y = (u0 < U && 2 * k + 1 < Cin) ? W[u0 * Cin + 2 * k + 1] : 0.f;
-        w1[k].x = (u1 < U && 2 * k < Cin) ? W[u1 * Cin + 2 * k] : 0.f;
-        w1[k].y = (u1 < U && 2 * k + 1 < Cin) ? W[u1 * Cin + 2 * k + 1] : 0.f;
+    for (int k = 0; k < Cin; ++k) {
+        w0[k] = u0 < U ? W[u0 * Cin + k] : 0.f;
+        w1[k] = u1 < U ? W[u1 * Cin + k] : 0.f;
     }
     const float sc0 = u0 < U ? scale[u0] : 0.f, sh0 = u0 < U ? shift[u0] : 0.f;
     const float sc1 = u1 < U ? scale[u1] : 0.f, sh1 = u1 < U ? shift[u1] : 0.f;
@@ -213,6 +199,8 @@ pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const floa
     const bool vec4 = (C == 4) && ((reinterpret_cast<uintptr_t>(a.voxels) & 15) == 0);
     for (int64_t m = (int64_t)blockIdx.x * PIL_WARPS + warp; m < M; m += (int64_t)gridDim.x * PIL_WARPS) {
         const int n = load_num(a, m);
+        int cx, cy;
+        load_xy(a, m, cx, cy);
         // ---- decorate: lane = slot
         float f[PFN_LDI];
 #pragma unroll
@@ -237,8 +225,6 @@ pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const floa
         }
         const float nf = (float)n;
         const float mx_ = __fdiv_rn(sx, nf), my_ = __fdiv_rn(sy, nf), mz_ = __fdiv_rn(sz, nf);
-        int cx, cy;
-        load_xy(a, m, cx, cy);
         const float pcx = __fadd_rn(__fmul_rn((float)cx, a.vx), a.x_off);   // :500-503
         const float pcy = __fadd_rn(__fmul_rn((float)cy, a.vy), a.y_off);   // :505-508
         const float x = f[0], y = f[1], z = f[2];
@@ -267,16 +253,17 @@ pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const floa
         for (int p = 0; p < p_end; ++p) {
             const float4 *f4 = reinterpret_cast<const float4 *>(row + p * PFN_LDI);
             const float4 fa = f4[0], fb = f4[1], fc = f4[2];
-            const float2 g[6] = {make_float2(fa.x, fa.y), make_float2(fa.z, fa.w), make_float2(fb.x, fb.y),
-                                 make_float2(fb.z, fb.w), make_float2(fc.x, fc.y), make_float2(fc.z, fc.w)};
-            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+            const float g[PFN_LDI] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w, fc.x, fc.y, fc.z, fc.w};
+            // scalar FMAs: on sm_100 the packed fma.rn.f32x2 issues at a quarter of the FFMA rate (measured: the
+            // packed form of this loop stalled on math_pipe_throttle at 0.5 issues per cycle)
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int k = 0; k < NP; ++k) {
-                a0 = ffma2(g[k], w0[k], a0);
-                a1 = ffma2(g[k], w1[k], a1);
+            for (int k = 0; k < Cin; ++k) {
+                a0 = __fmaf_rn(g[k], w0[k], a0);
+                a1 = __fmaf_rn(g[k], w1[k], a1);
             }
-            mx0 = fmaxf(mx0, __fmaf_rn(a0.x + a0.y, sc0, sh0));
-            mx1 = fmaxf(mx1, __fmaf_rn(a1.x + a1.y, sc1, sh1));
+            mx0 = fmaxf(mx0, __fmaf_rn(a0, sc0, sh0));
+            mx1 = fmaxf(mx1, __fmaf_rn(a1, sc1, sh1));
         }
         float *o = out + m * out_w;
         if (u0 < U) o[u0] = mx0;
