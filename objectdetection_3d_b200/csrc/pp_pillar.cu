@@ -174,7 +174,7 @@ constexpr int PFN_LDI = 12;
 // staged for the broadcast reads), lane = channel pair while multiplying.  The mean is a shuffle tree here (T1; the
 // bit-exact sequential form is decorate_row, used by pp_decorate and the generic layer kernel).
 template <int CIN>
-__global__ void __launch_bounds__(PIL_THREADS, 10)
+__global__ void __launch_bounds__(PIL_THREADS, 6)
 pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const float *__restrict__ scale,
                        const float *__restrict__ shift, int U, float *__restrict__ out)
 {
@@ -249,7 +249,7 @@ pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const floa
         // the running max at 0 (or relu(shift)) makes the explicit relu redundant.
         float mx0 = (p_end < P) ? fmaxf(sh0, 0.f) : 0.f;
         float mx1 = (p_end < P) ? fmaxf(sh1, 0.f) : 0.f;
-#pragma unroll 2
+#pragma unroll 4
         for (int p = 0; p < p_end; ++p) {
             const float4 *f4 = reinterpret_cast<const float4 *>(row + p * PFN_LDI);
             const float4 fa = f4[0], fb = f4[1], fc = f4[2];
@@ -479,7 +479,7 @@ extern "C" int pp_pillar_features(const float *voxels, const void *num_points, i
         size_t smem = (size_t)PIL_WARPS * 32 * PFN_LDI * sizeof(float);
         int64_t want = ceil_div(M, PIL_WARPS);
         // one resident wave that leaves room on every SM for the canvas kernel's early (pre-wait) zero fill
-        const unsigned grid = (unsigned)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
+        const unsigned grid = (unsigned)(want < 148 * 6 ? (want > 0 ? want : 1) : 148 * 6);
         cudaStream_t st = (cudaStream_t)stream;
         switch (C + 5) {
         case 8: launch_pdl(pfn_fused_small_kernel<8>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;

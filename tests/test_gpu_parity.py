@@ -27,7 +27,7 @@ def cu(a, dtype=None):
 
 
 # ------------------------------------------------------------------------------------------ sort
-@pytest.mark.parametrize("n", [1, 31, 2048, 2049, 100_003, 1_000_000])
+@pytest.mark.parametrize("n", [1, 31, 500, 2048, 2049, 4096, 4097, 20_000, 100_003, 1_000_000])
 def test_radix_sort_stable(pp, n):
     import ctypes
     from objectdetection_3d_b200 import _lib
