@@ -37,7 +37,7 @@ WORKLOAD = "D1M tile (1e6 pts, 0.16 m pillars, 12000x32, 432x496 canvas, reflect
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
@@ -327,9 +327,12 @@ def run_ours(args):
         return ms
 
     # ---- headline: device-resident inputs, K frames, N_SLOTS in flight ---------------------------
-    run_in_flight(max(W, 2 * N_SLOTS), "resident")
+    # the clock sampler (nvidia-smi -lms 100) needs a few hundred ms to start: launch it before the warm-up so that it
+    # is sampling by the time the timed region runs; it is stopped right after the timed region
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
                            os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
+    run_in_flight(max(W, 2 * N_SLOTS), "resident")
+    run_in_flight(max(K // 2, 2 * N_SLOTS), "resident")          # untimed, keeps the GPU under load while it starts
     l0 = _lib.launch_count()
     enqueue(slots[0], 0, "resident", stream)                    # count this library's kernels in one frame
     torch.cuda.synchronize()
@@ -434,13 +437,13 @@ def run_ours(args):
         per_launch_b = kbytes.get(dom, 0)
         ach = per_launch_b / (kern[dom]["avg_us"] * 1e-6) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": 19.06e6 if dom == "vox_scatter_kernel" else None,
+                    "frac": ach / hbm_peak, "traffic": 18.98e6 if dom == "vox_scatter_kernel" else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_b,
                     "avg_launch_us": kern[dom]["avg_us"],
                     "share_of_step": kern[dom]["ms_per_step"] / max(sum(v["ms_per_step"] for v in kern.values()), 1e-9),
                     "how": "CUDA events on the launching stream around every launch (pp_profile_*), separate single-"
                            "stream pass of %d steps after the timed region; traffic = dram read+write of one "
-                           "ncu --set full capture (profiles/r01_ncu_vox_scatter_full.txt)" % prof_steps}
+                           "ncu --set full capture (profiles/r01_ncu_frame_full_v3.md)" % prof_steps}
     stage_roof = {
         "voxelize": {"algorithmic_MB": vox_b / 1e6, "us": 1e3 * t_vox, "GBps": vox_b / (t_vox * 1e-3) / 1e9,
                      "frac": vox_b / (t_vox * 1e-3) / 1e9 / hbm_peak},
