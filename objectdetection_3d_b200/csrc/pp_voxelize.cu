@@ -66,9 +66,9 @@ struct VoxBuf {
     int32_t *pid_of_q;     // [Q]
     int32_t *bin_of_q;     // [Q]
     uint8_t *sat_of_q;     // [Q] first chunk whose inclusive prefix reaches max_points (NCHUNK if none)
-    uint8_t *tick;         // [N] arrival index of the point inside its (cell, chunk), saturated at 255
-    int32_t *q_of_point;   // [N]
-    uint32_t *key_of_point;  // [N] primary key (64-bit mode only)
+    uint16_t *tick;        // [N] (chunk << 8) | arrival index of the point inside its (cell, chunk), saturated at 255
+    int32_t *q_of_point;   // [N] row of the point's cell, -1 outside the grid (32-bit keys)
+    int2 *qk_of_point;     // [N] (row, primary key) in one 8-byte record (64-bit keys)
     int32_t *hist, *fill;  // [NFINE] each
     int32_t *list;         // [Q] cells in bucket order
     void *lkey;            // [Q] their first keys, same order
@@ -76,29 +76,45 @@ struct VoxBuf {
     u64 *coarse, *fine;    // splitters (64-bit mode): [NCHUNK-1], [NFINE-1]
 };
 
-// Cell index along one axis, bit-identical to the reference's floor((p - r) / v) in its promotion regime.
-// An fp32 reciprocal-multiply estimate decides every point that is not within a guard band of a cell
-// boundary (the band covers the rounding of r, 1/v and the two fp32 operations); only points inside the band
-// execute the reference's exact fp64 / IEEE-fp32 division.
-__device__ __forceinline__ bool axis_cell(const VoxParams &q, int j, float p, int &c)
+// Cell index along one axis, bit-identical to the reference's floor((p - r) / v) in its promotion regime: the exact
+// evaluation (fp64 / IEEE-fp32 division), used for points within a guard band of a cell boundary.
+__device__ __forceinline__ bool axis_cell_exact(const VoxParams &q, int j, float p, int &c)
 {
-    const float est = (p - q.rf[j]) * q.inv_vf[j];
-    const float fl = floorf(est);
-    const float fr = est - fl;
-    const float band = 1e-6f * (fabsf(est) + q.rv_abs[j]) + 1e-6f;
-    float cf = fl;
-    if (!(fr > band && fr < 1.0f - band)) {          // near a boundary (or NaN / huge): exact evaluation
-        double cd;
-        if (q.regime == 2) cd = floor(((double)p - q.r[j]) / q.v[j]);
-        else if (q.regime == 1) cd = floor((double)__fsub_rn(p, q.rf[j]) / q.v[j]);
-        else cd = (double)floorf(__fdiv_rn(__fsub_rn(p, q.rf[j]), q.vf[j]));
-        if (!(cd >= 0.0) || cd >= (double)q.g[j]) return false;   // also rejects NaN
-        c = (int)cd;
-        return true;
-    }
-    if (!(cf >= 0.f) || cf >= (float)q.g[j]) return false;
-    c = (int)cf;
+    double cd;
+    if (q.regime == 2) cd = floor(((double)p - q.r[j]) / q.v[j]);
+    else if (q.regime == 1) cd = floor((double)__fsub_rn(p, q.rf[j]) / q.v[j]);
+    else cd = (double)floorf(__fdiv_rn(__fsub_rn(p, q.rf[j]), q.vf[j]));
+    if (!(cd >= 0.0) || cd >= (double)q.g[j]) return false;   // also rejects NaN
+    c = (int)cd;
     return true;
+}
+
+// Linear cell of a point, or -1 outside the grid.  An fp32 reciprocal-multiply estimate decides every point that is
+// not within a guard band of a cell boundary on any axis (the band covers the rounding of r, 1/v and the two fp32
+// operations; outside it both floors agree); only those points take the exact path.  One branch per point.
+__device__ __forceinline__ int32_t point_cell(const VoxParams &q, float x, float y, float z)
+{
+    const float p[3] = {x, y, z};
+    float fl[3];
+    bool near = false, inside = true;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float est = (p[j] - q.rf[j]) * q.inv_vf[j];
+        fl[j] = floorf(est);
+        const float fr = est - fl[j];
+        const float band = 1e-6f * (fabsf(est) + q.rv_abs[j]) + 1e-6f;
+        near = near || !(fr > band && fr < 1.0f - band);          // also true for NaN / huge values
+        inside = inside && (fl[j] >= 0.f) && (fl[j] < (float)q.g[j]);
+    }
+    int cx, cy, cz;
+    if (near) {
+        if (!(axis_cell_exact(q, 0, x, cx) && axis_cell_exact(q, 1, y, cy) && axis_cell_exact(q, 2, z, cz))) return -1;
+    } else {
+        if (!inside) return -1;
+        cx = (int)fl[0]; cy = (int)fl[1]; cz = (int)fl[2];
+    }
+    // cell linearisation (z*gy + y)*gx + x = the (D,H,W) order of the BEV canvas
+    return (cz * q.g[1] + cy) * q.g[0] + cx;
 }
 
 // number of splitters <= k (upper bound): a monotone map key -> [0, n]
@@ -240,12 +256,10 @@ __device__ __forceinline__ void load_coarse(CoarseTable &t, const u64 *coarse)
 }
 __device__ __forceinline__ int coarse_chunk(const CoarseTable &t, uint32_t prim, uint32_t idx)
 {
-    int lo = 0, hi = NCHUNK - 1;          // upper bound over the 63 real splitters
+    // upper bound over the 63 real splitters (entry 63 is +inf), six fixed steps, no branches
+    int lo = 0;
 #pragma unroll
-    for (int it = 0; it < 6; ++it) {
-        const int mid = (lo + hi) >> 1;
-        if (lo < hi) { if (t.hi[mid] <= prim) lo = mid + 1; else hi = mid; }
-    }
+    for (int step = NCHUNK / 2; step > 0; step >>= 1) lo += (t.hi[lo + step - 1] <= prim) ? step : 0;
     while (lo > 0 && t.hi[lo - 1] == prim && t.lo[lo - 1] > idx) --lo;     // equal reflectance bits: order by index
     return lo;
 }
@@ -284,37 +298,38 @@ vox_scatter_kernel(const float *__restrict__ points, int64_t n, const VoxParams 
                 x = __ldg(pt); y = __ldg(pt + 1); z = __ldg(pt + 2);
                 if (WIDE) refl[k] = __ldg(pt + 3);
             }
-            int cx, cy, cz;
-            // cell linearisation (z*gy + y)*gx + x = the (D,H,W) order of the BEV canvas
-            if (axis_cell(prm, 0, x, cx) && axis_cell(prm, 1, y, cy) && axis_cell(prm, 2, z, cz))
-                cell[k] = (cz * prm.g[1] + cy) * prm.g[0] + cx;
+            cell[k] = point_cell(prm, x, y, z);
         }
         int q[SC_IT];
 #pragma unroll
         for (int k = 0; k < SC_IT; ++k) q[k] = cell[k] >= 0 ? w.map[cell[k]] : -1;      // L1 look (see claim_row)
-        int t[SC_IT];
+        int t[SC_IT], chk[SC_IT];
+        uint32_t prim[SC_IT];
 #pragma unroll
         for (int k = 0; k < SC_IT; ++k) {
             const int64_t p = p0 + k * VOX_THREADS;
             t[k] = 0;
+            chk[k] = 0;
+            prim[k] = 0;
             if (cell[k] < 0) continue;
             if (q[k] < 0) q[k] = claim_row(w, cell[k]);
-            int ch;
             if (WIDE) {
-                const uint32_t prim = ~ordered_bits(refl[k]);
-                w.key_of_point[p] = prim;
-                ch = coarse_chunk(s_ct, prim, (uint32_t)p);
+                prim[k] = ~ordered_bits(refl[k]);
+                chk[k] = coarse_chunk(s_ct, prim[k], (uint32_t)p);
             } else {
-                ch = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
+                chk[k] = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
             }
-            t[k] = atomicAdd(w.cnt + (size_t)q[k] * NCHUNK + ch, 1);
+            t[k] = atomicAdd(w.cnt + (size_t)q[k] * NCHUNK + chk[k], 1);
         }
+        // per point: (row, primary key) as one 8-byte record, and (chunk, ticket) as one 16-bit word
 #pragma unroll
         for (int k = 0; k < SC_IT; ++k) {
             const int64_t p = p0 + k * VOX_THREADS;
             if (p >= n) continue;
-            w.q_of_point[p] = cell[k] >= 0 ? q[k] : -1;
-            if (cell[k] >= 0) w.tick[p] = (uint8_t)(t[k] < 255 ? t[k] : 255);
+            const int qq = cell[k] >= 0 ? q[k] : -1;
+            if (WIDE) w.qk_of_point[p] = make_int2(qq, (int)prim[k]);
+            else w.q_of_point[p] = qq;
+            if (cell[k] >= 0) w.tick[p] = (uint16_t)((chk[k] << 8) | (t[k] < 255 ? t[k] : 255));
         }
     }
 }
@@ -379,10 +394,8 @@ template <typename K>
 __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, const VoxParams prm, const VoxBuf w)
 {
     pdl_enter();
-    __shared__ CoarseTable s_ct;
     __shared__ __align__(16) uint8_t s_sat[PLACE_TABLE];
     constexpr bool WIDE = sizeof(K) == 8;
-    if (WIDE) load_coarse(s_ct, w.coarse);
     const int nq = w.counters[0];
     const int ntab = nq < PLACE_TABLE ? nq : PLACE_TABLE;
     for (int i = threadIdx.x; i * 16 < ntab; i += PLACE_THREADS)
@@ -391,7 +404,7 @@ __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, con
     const int P = prm.P;
     // Four points per thread and iteration: their loads, and later their insertion chains, are issued back to back
     // (an in-order warp stalls at the first use of a result, so one point at a time would serialise every L2 round
-    // trip of the chain).
+    // trip of the chain).  The scatter kernel left (row, primary key) and (chunk, ticket) per point.
     constexpr int IT = 4;
     const int64_t stride = (int64_t)gridDim.x * PLACE_THREADS;
     for (int64_t p0 = (int64_t)blockIdx.x * PLACE_THREADS + threadIdx.x; p0 < n; p0 += stride * IT) {
@@ -400,9 +413,14 @@ __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, con
 #pragma unroll
         for (int k = 0; k < IT; ++k) {
             const int64_t p = p0 + k * stride;
-            q[k] = p < n ? w.q_of_point[p] : -1;
-            tk[k] = p < n ? (int)w.tick[p] : 0;
-            prim[k] = (WIDE && p < n) ? w.key_of_point[p] : 0u;
+            q[k] = -1;
+            tk[k] = 0;
+            prim[k] = 0u;
+            if (p < n) {
+                if (WIDE) { const int2 r = w.qk_of_point[p]; q[k] = r.x; prim[k] = (uint32_t)r.y; }
+                else q[k] = w.q_of_point[p];
+                tk[k] = (int)w.tick[p];
+            }
         }
         K key[IT];
         int ch[IT], base[IT], end[IT];
@@ -413,15 +431,10 @@ __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, con
             act[k] = q[k] >= 0;
             base[k] = end[k] = 0;
             key[k] = 0;
-            ch[k] = 0;
+            ch[k] = tk[k] >> 8;
+            tk[k] &= 0xFF;
             if (!act[k]) continue;
-            if (WIDE) {
-                key[k] = (K)(((u64)prim[k] << 32) | (uint32_t)p);
-                ch[k] = coarse_chunk(s_ct, prim[k], (uint32_t)p);
-            } else {
-                key[k] = (K)(uint32_t)p;
-                ch[k] = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
-            }
+            key[k] = WIDE ? (K)(((u64)prim[k] << 32) | (uint32_t)p) : (K)(uint32_t)p;
             const int sat = q[k] < PLACE_TABLE ? (int)s_sat[q[k]] : (int)w.sat_of_q[q[k]];
             if (ch[k] > sat) { act[k] = false; continue; }      // the pillar is full before this chunk (:303)
             const int32_t *incl = w.cnt + (size_t)q[k] * NCHUNK;
@@ -792,9 +805,9 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
     r.b.pid_of_q = a.take<int32_t>((size_t)r.Q);
     r.b.bin_of_q = a.take<int32_t>((size_t)r.Q);
     r.b.sat_of_q = a.take<uint8_t>((size_t)r.Q);
-    r.b.q_of_point = a.take<int32_t>((size_t)n1);
-    r.b.tick = a.take<uint8_t>((size_t)n1);
-    r.b.key_of_point = wide ? a.take<uint32_t>((size_t)n1) : nullptr;
+    r.b.q_of_point = wide ? nullptr : a.take<int32_t>((size_t)n1);
+    r.b.qk_of_point = wide ? a.take<int2>((size_t)n1) : nullptr;
+    r.b.tick = a.take<uint16_t>((size_t)n1);
     r.b.list = a.take<int32_t>((size_t)r.Q);
     r.b.lkey = a.take<char>((size_t)r.Q * ksz);
     r.b.q_of_pid = a.take<int32_t>((size_t)max_rows_of(n, c));
