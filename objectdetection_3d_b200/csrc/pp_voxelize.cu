@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(1024)
 vox_init_kernel(const float *__restrict__ points, int64_t n, int C, int wide, u64 *__restrict__ coarse,
                 u64 *__restrict__ fine, const InitArgs ia)
 {
-    pdl_enter();
+    // First kernel of the call: wait for everything earlier on the stream, THEN let the scatter kernel start -- its
+    // CTAs read `points` before their own dependency wait, which is only safe once the producer of the points is done.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x;
     if (blockIdx.x > 0 || !wide) {
         const int64_t nb = gridDim.x - (wide ? 1 : 0), b = blockIdx.x - (wide ? 1 : 0);
@@ -271,13 +274,12 @@ __global__ void __launch_bounds__(VOX_THREADS)
 vox_scatter_kernel(const float *__restrict__ points, int64_t n, const VoxParams prm, const int32_t *__restrict__ perm,
                    const VoxBuf w)
 {
-    pdl_enter();
+    // PDL: the first batch of points is read and binned into cells BEFORE the dependency wait, i.e. while the init
+    // kernel (workspace fill, sample sort) is still running; nothing the init kernel writes is touched before it.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ CoarseTable s_ct;
     constexpr bool WIDE = sizeof(K) == 8;
-    if (WIDE) {
-        load_coarse(s_ct, w.coarse);
-        __syncthreads();
-    }
+    bool waited = false;
     for (int64_t b0 = (int64_t)blockIdx.x * (VOX_THREADS * SC_IT); b0 < n; b0 += (int64_t)gridDim.x * (VOX_THREADS * SC_IT)) {
         const int64_t p0 = b0 + threadIdx.x;
         int32_t cell[SC_IT];
@@ -299,6 +301,14 @@ vox_scatter_kernel(const float *__restrict__ points, int64_t n, const VoxParams 
                 if (WIDE) refl[k] = __ldg(pt + 3);
             }
             cell[k] = point_cell(prm, x, y, z);
+        }
+        if (!waited) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            if (WIDE) {
+                load_coarse(s_ct, w.coarse);
+                __syncthreads();
+            }
+            waited = true;
         }
         int q[SC_IT];
 #pragma unroll
