@@ -197,17 +197,32 @@ vox_init_kernel(const float *__restrict__ points, int64_t n, int C, int wide, u6
         s[i] = k;
     }
     __syncthreads();
-    for (int size = 2; size <= SAMPLE; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < SAMPLE / 2; t += 1024) {
-                int lo = 2 * t - (t & (stride - 1));
-                int hi = lo + stride;
-                bool up = (lo & size) == 0;
-                u64 a = s[lo], b = s[hi];
-                if ((a > b) == up) { s[lo] = b; s[hi] = a; }
+    {
+        // bitonic sort, one key per thread (SAMPLE == blockDim): partners less than a warp apart exchange with
+        // shuffles (40 of the 55 steps), the others through shared memory
+        u64 k = s[tid];
+        for (int size = 2; size <= SAMPLE; size <<= 1) {
+            const bool up = (tid & size) == 0;
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                u64 o;
+                if (stride >= 32) {
+                    __syncthreads();
+                    s[tid] = k;
+                    __syncthreads();
+                    o = s[tid ^ stride];
+                } else {
+                    const unsigned lo = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)k, stride);
+                    const unsigned hi = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)(k >> 32), stride);
+                    o = ((u64)hi << 32) | lo;
+                }
+                const bool lower = (tid & stride) == 0;
+                const bool take_min = lower == up;
+                k = take_min ? (k < o ? k : o) : (k < o ? o : k);
             }
-            __syncthreads();
         }
+        __syncthreads();
+        s[tid] = k;
+        __syncthreads();
     }
     // coarse chunk b starts at the geometric quantile geo_sample_index(b); splitter i is the start of chunk i + 1
     for (int i = tid; i < NCHUNK - 1; i += 1024) coarse[i] = s[geo_sample_index<C_OCT, C_SUB>(i + 1, SAMPLE)];
