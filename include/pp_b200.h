@@ -96,6 +96,25 @@ PP_API int pp_voxelize(const float *points, int64_t n_points, const pp_voxel_cfg
                 int32_t *voxel_num, int32_t *pillar_map, void *workspace, size_t workspace_bytes,
                 pp_stream_t stream);
 
+/*
+ * pp_voxelize fused with the single-layer PillarFeatureNet (pp_pillar_features below): the warp that gathers a pillar
+ * also decorates it and runs it through Linear + BN + ReLU + max while its points are still in registers, so the frame
+ * has one launch less and the voxels are not read back.  Same outputs as pp_voxelize followed by pp_pillar_features
+ * (bit-identical features); feat (rows, units + 1).  Needs num_feats == 4, max_points <= 32, units <= 64.
+ */
+typedef struct {
+    const float *weight;  /* (units, 9) */
+    const float *scale;   /* (units) BatchNorm folded: gamma / sqrt(var + eps) */
+    const float *shift;   /* (units) beta - mean * scale */
+    int32_t units;
+    float vx, vy, x_off, y_off; /* pillar centre = cell * v + off, model/PointPillars.py:500-508 */
+    float *feat;
+} pp_pfn_fused;
+PP_API int pp_voxelize_features(const float *points, int64_t n_points, const pp_voxel_cfg *cfg, int order,
+                         const int32_t *perm, float *voxels, int32_t *coors, int32_t *num_points,
+                         int32_t *voxel_num, int32_t *pillar_map, const pp_pfn_fused *pfn, void *workspace,
+                         size_t workspace_bytes, pp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Stage 2 -- pillar decoration, PFN and dense scatter.
  * ---------------------------------------------------------------------------------------- */

@@ -38,6 +38,8 @@ SIGNATURES = {
     "pp_voxelize_max_rows": (_i64, [_i64, _cfgp]),
     "pp_voxelize_workspace_bytes": (_sz, [_i64, _cfgp, ctypes.c_int]),
     "pp_voxelize": (ctypes.c_int, [_vp, _i64, _cfgp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pp_voxelize_features": (ctypes.c_int, [_vp, _i64, _cfgp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                            _vp]),
     "pp_decorate": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _vp, ctypes.c_int, ctypes.c_int,
                                    _f32, _f32, _f32, _f32, _vp, _vp]),
     "pp_pfn_layer": (ctypes.c_int, [_vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int,
@@ -80,6 +82,13 @@ SIGNATURES = {
 }
 
 _lib = None
+
+
+class PfnFused(ctypes.Structure):
+    """pp_pfn_fused of include/pp_b200.h"""
+    _fields_ = [("weight", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
+                ("units", ctypes.c_int32), ("vx", ctypes.c_float), ("vy", ctypes.c_float), ("x_off", ctypes.c_float),
+                ("y_off", ctypes.c_float), ("feat", ctypes.c_void_p)]
 
 
 class PPError(RuntimeError):

@@ -8,6 +8,7 @@
 #include <math_constants.h>
 
 #include "pp_common.cuh"
+#include "pp_pillar.cuh"
 
 namespace pp {
 namespace {
@@ -165,14 +166,8 @@ pfn_kernel(const PillarIn a, const float *__restrict__ W, const float *__restric
     }
 }
 
-// Fast path of the fused single-layer PillarFeatureNet (Cin <= 12, U <= 64): the two weight rows a lane owns live
-// in registers for the whole grid-stride loop, the decorated row is read back as broadcast 128-bit shared loads.
-// Dot products use FMAs (T1 against the reference's sgemm; pp_decorate's decoration stays bit-exact).
-constexpr int PFN_LDI = 12;
-
-// P <= 32: lane = slot while decorating (the pillar's points never leave registers until the decorated row is
-// staged for the broadcast reads), lane = channel pair while multiplying.  The mean is a shuffle tree here (T1; the
-// bit-exact sequential form is decorate_row, used by pp_decorate and the generic layer kernel).
+// Fast path of the fused single-layer PillarFeatureNet (Cin <= 12, U <= 64, P <= 32): the two weight rows a lane owns
+// live in registers for the whole grid-stride loop; the per-pillar work is pfn_pillar (pp_pillar.cuh).
 template <int CIN>
 __global__ void __launch_bounds__(PIL_THREADS, 6)
 pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const float *__restrict__ scale,
@@ -182,17 +177,9 @@ pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const floa
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int P = a.P, C = a.C;
-    constexpr int Cin = CIN;
     float *row = smem + warp * 32 * PFN_LDI;
-    float w0[CIN], w1[CIN];
-    const int u0 = lane, u1 = lane + 32;
-#pragma unroll
-    for (int k = 0; k < Cin; ++k) {
-        w0[k] = u0 < U ? W[u0 * Cin + k] : 0.f;
-        w1[k] = u1 < U ? W[u1 * Cin + k] : 0.f;
-    }
-    const float sc0 = u0 < U ? scale[u0] : 0.f, sh0 = u0 < U ? shift[u0] : 0.f;
-    const float sc1 = u1 < U ? scale[u1] : 0.f, sh1 = u1 < U ? shift[u1] : 0.f;
+    PfnWeights<CIN> pw;
+    pfn_load_weights<CIN>(pw, W, scale, shift, U, lane);
     int64_t M = a.M;
     if (a.m_dev) { int64_t md = *a.m_dev; M = md < M ? md : M; }
     const int out_w = U + 1;
@@ -201,7 +188,6 @@ pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const floa
         const int n = load_num(a, m);
         int cx, cy;
         load_xy(a, m, cx, cy);
-        // ---- decorate: lane = slot
         float f[PFN_LDI];
 #pragma unroll
         for (int k = 0; k < PFN_LDI; ++k) f[k] = 0.f;
@@ -216,60 +202,7 @@ pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const floa
                     if (k < C) f[k] = __ldg(v + k);
             }
         }
-        float sx = f[0], sy = f[1], sz = f[2];                  // zero padded slots add nothing (:493-494)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sx += __shfl_xor_sync(0xFFFFFFFFu, sx, o);
-            sy += __shfl_xor_sync(0xFFFFFFFFu, sy, o);
-            sz += __shfl_xor_sync(0xFFFFFFFFu, sz, o);
-        }
-        const float nf = (float)n;
-        const float mx_ = __fdiv_rn(sx, nf), my_ = __fdiv_rn(sy, nf), mz_ = __fdiv_rn(sz, nf);
-        const float pcx = __fadd_rn(__fmul_rn((float)cx, a.vx), a.x_off);   // :500-503
-        const float pcy = __fadd_rn(__fmul_rn((float)cy, a.vy), a.y_off);   // :505-508
-        const float x = f[0], y = f[1], z = f[2];
-#pragma unroll
-        for (int k = 0; k < PFN_LDI - 5; ++k)
-            if (k == C) {                                        // C is 3..7 here (C + 5 == CIN)
-                f[k + 0] = __fsub_rn(x, mx_);                    // :496
-                f[k + 1] = __fsub_rn(y, my_);
-                f[k + 2] = __fsub_rn(z, mz_);
-                f[k + 3] = __fsub_rn(x, pcx);
-                f[k + 4] = __fsub_rn(y, pcy);
-            }
-        // slots >= n are never read below (p_end), so the padding mask (:518-521) needs no multiply
-        float4 *r4 = reinterpret_cast<float4 *>(row + lane * PFN_LDI);
-        r4[0] = make_float4(f[0], f[1], f[2], f[3]);
-        r4[1] = make_float4(f[4], f[5], f[6], f[7]);
-        r4[2] = make_float4(f[8], f[9], f[10], f[11]);
-        __syncwarp();
-        // ---- multiply: lane = channels (lane, lane + 32)
-        const int p_end = n < P ? n : P;
-        // zero-padded slots take part in the max (:403-410): they contribute relu(shift).  relu(y) >= 0, so starting
-        // the running max at 0 (or relu(shift)) makes the explicit relu redundant.
-        float mx0 = (p_end < P) ? fmaxf(sh0, 0.f) : 0.f;
-        float mx1 = (p_end < P) ? fmaxf(sh1, 0.f) : 0.f;
-#pragma unroll 4
-        for (int p = 0; p < p_end; ++p) {
-            const float4 *f4 = reinterpret_cast<const float4 *>(row + p * PFN_LDI);
-            const float4 fa = f4[0], fb = f4[1], fc = f4[2];
-            const float g[PFN_LDI] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w, fc.x, fc.y, fc.z, fc.w};
-            // scalar FMAs: on sm_100 the packed fma.rn.f32x2 issues at a quarter of the FFMA rate (measured: the
-            // packed form of this loop stalled on math_pipe_throttle at 0.5 issues per cycle)
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < Cin; ++k) {
-                a0 = __fmaf_rn(g[k], w0[k], a0);
-                a1 = __fmaf_rn(g[k], w1[k], a1);
-            }
-            mx0 = fmaxf(mx0, __fmaf_rn(a0, sc0, sh0));
-            mx1 = fmaxf(mx1, __fmaf_rn(a1, sc1, sh1));
-        }
-        float *o = out + m * out_w;
-        if (u0 < U) o[u0] = mx0;
-        if (u1 < U) o[u1] = mx1;
-        if (lane == 0) o[U] = (float)n;                                       // :526
-        __syncwarp();
+        pfn_pillar<CIN>(pw, f, C, P, n, cx, cy, a.vx, a.vy, a.x_off, a.y_off, row, out + m * out_w, U, lane);
     }
 }
 

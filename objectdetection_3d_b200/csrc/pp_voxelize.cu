@@ -26,6 +26,7 @@
 #include <math_constants.h>
 
 #include "pp_common.cuh"
+#include "pp_pillar.cuh"
 
 namespace pp {
 namespace {
@@ -785,6 +786,72 @@ vox_gather_sorted_kernel(const float *__restrict__ points, const int32_t *__rest
     }
 }
 
+// Gather fused with the single-layer PillarFeatureNet (C == 4, P <= 32, float4 points): the warp that has just sorted
+// and gathered a pillar holds its points in registers in exactly the layout the PFN's decoration starts from (lane =
+// slot), so it writes `voxels` / `num_points` AND runs the pillar through pfn_pillar: the PFN kernel, its launch and its
+// re-read of the voxels disappear from the frame.
+struct PfnArgs {
+    const float *W, *scale, *shift;
+    float *feat;
+    int U;
+    float vx, vy, x_off, y_off;
+    int gx, gy;
+};
+
+constexpr int GP_THREADS = 128;      // 4 pillars per CTA
+
+template <typename K>
+__global__ void __launch_bounds__(GP_THREADS, 6)
+vox_gather_pfn_kernel(const float *__restrict__ points, const int32_t *__restrict__ perm, const VoxBuf w,
+                      const int32_t *__restrict__ voxel_num, int P, float *__restrict__ voxels,
+                      int32_t *__restrict__ num_points, const PfnArgs pa)
+{
+    // the weights do not depend on the predecessor: load them before the dependency wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __shared__ __align__(16) float s_row[(GP_THREADS / 32) * 32 * PFN_LDI];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PfnWeights<9> pw;
+    pfn_load_weights<9>(pw, pa.W, pa.scale, pa.shift, pa.U, lane);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int nvox = *voxel_num;
+    const K cutoff = *(const K *)w.cutoff;
+    float *row = s_row + warp * 32 * PFN_LDI;
+    for (int m = blockIdx.x * (GP_THREADS / 32) + warp; m < nvox; m += gridDim.x * (GP_THREADS / 32)) {
+        const int q = w.q_of_pid[m];
+        const K *krow = (const K *)w.rows + (size_t)q * P;
+        const int total = w.cnt[(size_t)q * NCHUNK + NCHUNK - 1];
+        const int cell = w.cell_of_q[q];
+        const int nk = total < P ? total : P;
+        K k0 = lane < nk ? krow[lane] : KeyInf<K>::value();
+        if (!(k0 < cutoff)) k0 = KeyInf<K>::value();
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int j = size >> 1; j > 0; j >>= 1) {
+                const K o = shfl_xor_key<K>(k0, j);
+                const bool take_min = ((lane & size) == 0) != ((lane & j) != 0);
+                k0 = take_min ? (k0 < o ? k0 : o) : (k0 < o ? o : k0);
+            }
+        }
+        const bool valid = k0 != KeyInf<K>::value();
+        const int n = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+        if (lane == 0) num_points[m] = n;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            const uint32_t pos = (uint32_t)k0;                   // low word = position / original index
+            const int64_t idx = perm ? (int64_t)(uint32_t)perm[pos] : (int64_t)pos;
+            v = __ldg(reinterpret_cast<const float4 *>(points) + idx);
+        }
+        if (lane < P) reinterpret_cast<float4 *>(voxels)[(int64_t)m * P + lane] = v;
+        float f[PFN_LDI];
+#pragma unroll
+        for (int k = 0; k < PFN_LDI; ++k) f[k] = 0.f;
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+        pfn_pillar<9>(pw, f, 4, P, n, cell % pa.gx, (cell / pa.gx) % pa.gy, pa.vx, pa.vy, pa.x_off, pa.y_off, row,
+                      pa.feat + (int64_t)m * (pa.U + 1), pa.U, lane);
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 int64_t max_rows_of(int64_t n, const pp_voxel_cfg *c)
 {
@@ -851,7 +918,8 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
 
 template <typename K>
 int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *perm, const Carve &cv, float *voxels,
-        int32_t *coors, int32_t *num_points, int32_t *voxel_num, int32_t *pillar_map, int64_t max_rows, cudaStream_t st)
+        int32_t *coors, int32_t *num_points, int32_t *voxel_num, int32_t *pillar_map, int64_t max_rows, const PfnArgs *pfn,
+        cudaStream_t st)
 {
     const VoxBuf &w = cv.b;
     constexpr bool WIDE = sizeof(K) == 8;
@@ -912,6 +980,12 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
         if (int rc = check_launch("vox_rank_kernel")) return rc;
     }
     const bool vec4 = prm.vec4 && ((uintptr_t)voxels % 16 == 0);
+    if (pfn) {
+        const int64_t want = ceil_div(max_rows, GP_THREADS / 32);
+        launch_pdl(vox_gather_pfn_kernel<K>, dim3((unsigned)(want < 148 * 6 ? want : 148 * 6)), dim3(GP_THREADS), 0, st, points,
+                   perm, w, (const int32_t *)voxel_num, prm.P, voxels, num_points, *pfn);
+        return check_launch("vox_gather_pfn_kernel");
+    }
     if (prm.ticket) {
         const unsigned gs = (unsigned)(ceil_div(max_rows, VOX_THREADS / 32) < 148 * 8 ? ceil_div(max_rows, VOX_THREADS / 32) : 148 * 8);
         if (prm.P <= 32)
@@ -950,9 +1024,34 @@ extern "C" size_t pp_voxelize_workspace_bytes(int64_t n_points, const pp_voxel_c
     return total;
 }
 
+static int voxelize_impl(const float *points, int64_t n, const pp_voxel_cfg *cfg, int order, const int32_t *perm,
+                         float *voxels, int32_t *coors, int32_t *num_points, int32_t *voxel_num, int32_t *pillar_map,
+                         const pp_pfn_fused *pfn, void *workspace, size_t workspace_bytes, pp_stream_t stream);
+
 extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *cfg, int order, const int32_t *perm,
                            float *voxels, int32_t *coors, int32_t *num_points, int32_t *voxel_num,
                            int32_t *pillar_map, void *workspace, size_t workspace_bytes, pp_stream_t stream)
+{
+    return voxelize_impl(points, n, cfg, order, perm, voxels, coors, num_points, voxel_num, pillar_map, nullptr, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" int pp_voxelize_features(const float *points, int64_t n, const pp_voxel_cfg *cfg, int order,
+                                    const int32_t *perm, float *voxels, int32_t *coors, int32_t *num_points,
+                                    int32_t *voxel_num, int32_t *pillar_map, const pp_pfn_fused *pfn, void *workspace,
+                                    size_t workspace_bytes, pp_stream_t stream)
+{
+    PP_REQUIRE(pfn && pfn->weight && pfn->scale && pfn->shift && pfn->feat, "null PFN arguments");
+    PP_REQUIRE(cfg && cfg->num_feats == 4 && cfg->max_points <= 32 && pfn->units >= 1 && pfn->units <= 64,
+               "the fused form needs C == 4, max_points <= 32, units <= 64 (else pp_voxelize + pp_pillar_features)");
+    PP_REQUIRE(((uintptr_t)points % 16 == 0) && ((uintptr_t)voxels % 16 == 0), "points / voxels must be 16-byte aligned");
+    return voxelize_impl(points, n, cfg, order, perm, voxels, coors, num_points, voxel_num, pillar_map, pfn, workspace,
+                         workspace_bytes, stream);
+}
+
+static int voxelize_impl(const float *points, int64_t n, const pp_voxel_cfg *cfg, int order, const int32_t *perm,
+                         float *voxels, int32_t *coors, int32_t *num_points, int32_t *voxel_num, int32_t *pillar_map,
+                         const pp_pfn_fused *pfn, void *workspace, size_t workspace_bytes, pp_stream_t stream)
 {
     pp::enter((cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1012,7 +1111,14 @@ extern "C" int pp_voxelize(const float *points, int64_t n, const pp_voxel_cfg *c
     }
     const int32_t *order_perm = order == PP_ORDER_PERM ? perm : nullptr;
     const int64_t max_rows = max_rows_of(n, cfg);
+    PfnArgs pa, *pap = nullptr;
+    if (pfn) {
+        pa.W = pfn->weight; pa.scale = pfn->scale; pa.shift = pfn->shift; pa.feat = pfn->feat; pa.U = pfn->units;
+        pa.vx = pfn->vx; pa.vy = pfn->vy; pa.x_off = pfn->x_off; pa.y_off = pfn->y_off;
+        pa.gx = cfg->grid[0]; pa.gy = cfg->grid[1];
+        pap = &pa;
+    }
     if (wide)
-        return run<u64>(points, n, q, order_perm, cv, voxels, coors, num_points, voxel_num, pillar_map, max_rows, st);
-    return run<uint32_t>(points, n, q, order_perm, cv, voxels, coors, num_points, voxel_num, pillar_map, max_rows, st);
+        return run<u64>(points, n, q, order_perm, cv, voxels, coors, num_points, voxel_num, pillar_map, max_rows, pap, st);
+    return run<uint32_t>(points, n, q, order_perm, cv, voxels, coors, num_points, voxel_num, pillar_map, max_rows, pap, st);
 }

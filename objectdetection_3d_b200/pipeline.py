@@ -53,6 +53,10 @@ class FramePipeline:
         self.vx, self.vy = vx, vy
         self.x_off = vx / 2 + geom["point_cloud_range"][0]
         self.y_off = vy / 2 + geom["point_cloud_range"][1]
+        # gather + PFN in one kernel (pp_voxelize_features) when the shapes allow it
+        self.fused = self.C == 4 and self.P <= 32 and self.U <= 64
+        self.pfn_args = _lib.PfnFused(self.w.data_ptr(), self.scale.data_ptr(), self.shift.data_ptr(), self.U,
+                                      self.vx, self.vy, self.x_off, self.y_off, self.feat.data_ptr())
 
     def new_canvas(self):
         return torch.empty((1, (self.U + 1) * self.D, self.H, self.W), dtype=torch.float32, device=self.device)
@@ -72,10 +76,27 @@ class FramePipeline:
         _lib.check(self.lib.pp_scatter_mapped(_ptr(self.feat), _ptr(self.pillar_map), self.U + 1, 1, self.D, self.H,
                                               self.W, _ptr(canvas), _sp(stream)))
 
-    def run(self, points, canvas, stream=None):
+    def voxelize_features(self, points, stream):
+        """voxelize + PillarFeatureNet: self.voxels / coors / num / voxel_num / pillar_map AND self.feat."""
+        n = points.shape[0]
+        assert self.fused and n <= self.n_points and points.shape[1] == self.C
+        _lib.check(self.lib.pp_voxelize_features(
+            _ptr(points), n, ctypes.byref(self.cfg), self.order, None, _ptr(self.voxels), _ptr(self.coors),
+            _ptr(self.num), _ptr(self.voxel_num), _ptr(self.pillar_map), ctypes.byref(self.pfn_args), _ptr(self.vox_ws),
+            self.vox_ws_bytes, _sp(stream)))
+
+    def scatter(self, canvas, stream):
+        _lib.check(self.lib.pp_scatter_mapped(_ptr(self.feat), _ptr(self.pillar_map), self.U + 1, 1, self.D, self.H,
+                                              self.W, _ptr(canvas), _sp(stream)))
+
+    def run(self, points, canvas, stream=None, fused=None):
         stream = stream or torch.cuda.current_stream()
-        self.voxelize(points, stream)
-        self.encode_scatter(canvas, stream)
+        if self.fused if fused is None else fused:
+            self.voxelize_features(points, stream)
+            self.scatter(canvas, stream)
+        else:
+            self.voxelize(points, stream)
+            self.encode_scatter(canvas, stream)
         return canvas
 
     # algorithmic bytes per frame (SURVEY.md section 8d): each boundary input read once, each output written once

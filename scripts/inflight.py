@@ -11,8 +11,9 @@ bs = [(torch.from_numpy(b).cuda(), torch.from_numpy(s).cuda()) for b, s in bs]
 slots = [dict(st=torch.cuda.Stream(), pipe=pipeline.FramePipeline(g, pfn, 1_000_000), nms=pipeline.NmsStage(20000)) for _ in range(S)]
 for sl in slots: sl["canvas"] = sl["pipe"].new_canvas()
 def enq(sl, i, what):
-    if "v" in what: sl["pipe"].voxelize(pts[i % 4], sl["st"])
-    if "e" in what: sl["pipe"].encode_scatter(sl["canvas"], sl["st"])
+    if "v" in what and "e" in what: sl["pipe"].run(pts[i % 4], sl["canvas"], sl["st"])      # gather + PFN fused
+    elif "v" in what: sl["pipe"].voxelize(pts[i % 4], sl["st"])
+    elif "e" in what: sl["pipe"].encode_scatter(sl["canvas"], sl["st"])
     if "n" in what: sl["nms"].run(bs[i % 4][0], bs[i % 4][1], 0.0, 0.1, 0, sl["st"])
 def run(K, what):
     graphs = []

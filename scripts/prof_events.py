@@ -17,10 +17,10 @@ nms = pipeline.NmsStage(20000)
 st = torch.cuda.current_stream()
 
 def once():
-    if what in ("vox", "enc", "frame"):
+    if what == "vox":
         pipe.voxelize(pts, st)
     if what in ("enc", "frame"):
-        pipe.encode_scatter(canvas, st)
+        pipe.run(pts, canvas, st, fused=("unfused" not in sys.argv))
     if what in ("nms", "frame"):
         nms.run(b, s, 0.0, 0.1, 0, st)
 

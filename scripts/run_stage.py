@@ -18,10 +18,10 @@ if what in ("nms", "frame"):
     nms = pipeline.NmsStage(20000)
 st = torch.cuda.current_stream()
 for _ in range(reps):
-    if what in ("vox", "enc", "frame"):
+    if what == "vox":
         pipe.voxelize(pts, st)
     if what in ("enc", "frame"):
-        pipe.encode_scatter(canvas, st)
+        pipe.run(pts, canvas, st)
     if what in ("nms", "frame"):
         nms.run(b, s, 0.0, 0.1, 0, st)
 torch.cuda.synchronize()

@@ -361,4 +361,12 @@ def test_frame_pipeline_full_size(pp, oracle, order):
     got = canvas.cpu().numpy()
     scale = float(np.abs(pts[:, :3]).max())
     assert_close_t1(got, ref, atol=1e-5 * scale * 4, what="canvas")
+    # the fused gather + PFN kernel (default) and the two separate kernels give bit-identical frames
+    feat_fused, vox_fused = pipe.feat[:m].clone(), pipe.voxels[:m].clone()
+    canvas2 = pipe.new_canvas()
+    assert pipe.fused
+    pipe.run(cu(pts), canvas2, fused=False)
+    torch.cuda.synchronize()
+    assert torch.equal(pipe.feat[:m], feat_fused) and torch.equal(pipe.voxels[:m], vox_fused)
+    assert torch.equal(canvas2, canvas)
     assert np.array_equal(got == 0, ref == 0) or np.abs(got[(got == 0) != (ref == 0)]).max() < 1e-4
