@@ -341,24 +341,56 @@ __device__ __forceinline__ float box3_inter_volume(const Box3 &a, const Box3 &b,
     dual3(pe, dp, gp);
     float sum_p = 0.f, sum_c = 0.f, poly[B3_MAXV][3];
     const float ax[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+    // Per face: the slab coordinates of its four vertices decide most cases without clipping -- all four beyond the
+    // same side of a slab: the face contributes nothing; all four inside every slab: its cone as it is; only faces
+    // that straddle a slab boundary go through Sutherland-Hodgman, and only against the slabs they straddle.
 #pragma unroll 1
     for (int f = 0; f < 6; ++f) {
         b3_face(po, pe, f, poly);
+        unsigned all_out = ~0u, any_out = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned oc = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                oc |= (poly[i][k] < -0.5f - eps) ? (1u << (2 * k)) : 0u;
+                oc |= (poly[i][k] > 0.5f + eps) ? (2u << (2 * k)) : 0u;
+            }
+            all_out &= oc;
+            any_out |= oc;
+        }
+        if (all_out & 0x3Fu) continue;
         int n = 4;
 #pragma unroll 1
-        for (int k = 0; k < 3 && n > 2; ++k) n = b3_clip(poly, n, ax[k], 0.f, -0.5f - eps, 0.5f + eps);
+        for (int k = 0; k < 3 && n > 2; ++k)
+            if ((any_out >> (2 * k)) & 3u) n = b3_clip(poly, n, ax[k], 0.f, -0.5f - eps, 0.5f + eps);
         if (n > 2) sum_p += b3_cone(poly, n);
     }
     const float co[3] = {-0.5f, -0.5f, -0.5f};
+    float offk[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) offk[k] = -(gp[k][0] * po[0] + gp[k][1] * po[1] + gp[k][2] * po[2]);
 #pragma unroll 1
     for (int f = 0; f < 6; ++f) {
         b3_face(co, ax, f, poly);
+        unsigned all_out = ~0u, any_out = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned oc = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float sk = gp[k][0] * poly[i][0] + gp[k][1] * poly[i][1] + gp[k][2] * poly[i][2] + offk[k];
+                oc |= (sk < eps) ? (1u << (2 * k)) : 0u;
+                oc |= (sk > 1.f - eps) ? (2u << (2 * k)) : 0u;
+            }
+            all_out &= oc;
+            any_out |= oc;
+        }
+        if (all_out & 0x3Fu) continue;
         int n = 4;
 #pragma unroll 1
-        for (int k = 0; k < 3 && n > 2; ++k) {
-            const float off = -(gp[k][0] * po[0] + gp[k][1] * po[1] + gp[k][2] * po[2]);
-            n = b3_clip(poly, n, gp[k], off, eps, 1.f - eps);
-        }
+        for (int k = 0; k < 3 && n > 2; ++k)
+            if ((any_out >> (2 * k)) & 3u) n = b3_clip(poly, n, gp[k], offk[k], eps, 1.f - eps);
         if (n > 2) sum_c += b3_cone(poly, n);
     }
     float v = ((dp < 0.f ? -sum_p : sum_p) + sum_c) * (1.f / 6.f) * vb;
