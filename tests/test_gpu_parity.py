@@ -252,6 +252,32 @@ def test_nms_full_size_vs_oracle(pp, oracle, n, extent):
             assert not (iou > np.float32(ithr)).any()
 
 
+def test_nms_empty_and_maximum_size(pp, oracle):
+    """N = 0, and the largest N the library accepts (131 072), checked through size-independent properties: descending
+    scores, no kept pair above the threshold (sampled), every dropped candidate overlaps a better kept box (sampled)."""
+    from objectdetection_3d_b200 import synth
+    empty = pp.model_utils.multiclass_nms(torch.zeros((0, 9), device="cuda"), torch.zeros((0, 2), device="cuda"), 0.1, 0.1, 2)
+    assert len(empty) == 2 and all(k.numel() == 0 and k.dtype == torch.int64 for k in empty)
+    n = 131_072
+    boxes, scores = synth.nms_boxes(n=n, seed=77, extent=300.0)
+    b, s = cu(boxes), cu(scores)
+    keep = pp.model_utils.multiclass_nms(b, s, 0.0, 0.1, 2)[0].cpu().numpy()
+    assert len(np.unique(keep)) == len(keep) and (np.diff(scores[keep, 0]) < 0).all() and len(keep) > 5_000
+    rect = pp.ops_torch.bbox2rotated_corners2D(b)
+    rng = np.random.default_rng(1)
+    sub = np.sort(rng.choice(len(keep), 3000, replace=False))
+    kk = pp.ops_torch.bbox_iou2D(rect[keep[sub]], rect[keep]).cpu().numpy()
+    kk[np.arange(len(sub)), sub] = 0
+    assert not (kk > np.float32(0.1)).any()
+    dropped = np.setdiff1d(np.arange(n), keep)
+    dsub = rng.choice(dropped, 2000, replace=False)
+    dk = pp.ops_torch.bbox_iou2D(rect[dsub], rect[keep]).cpu().numpy()
+    better = scores[keep, 0][None, :] > scores[dsub, 0][:, None]
+    assert ((dk > np.float32(0.1)) & better).any(axis=1).all()
+    with pytest.raises(ValueError):
+        pp.model_utils.multiclass_nms(torch.zeros((131_073, 9), device="cuda"), torch.zeros((131_073, 1), device="cuda"), 0.1, 0.1, 2)
+
+
 def test_head_golden(pp):
     """Anchor3DHead.get_bboxes_single / assign_bboxes against the reference's outputs."""
     from objectdetection_3d_b200 import synth
