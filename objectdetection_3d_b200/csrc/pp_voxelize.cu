@@ -24,6 +24,8 @@
 //   D  vox_gather*_kernel     per pillar: sort the row, drop keys >= cutoff, voxels[m][s] = points[row[s]]
 // Everything but the 16 B/point read and the output write is L2-resident workspace traffic.
 #include <math_constants.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "pp_common.cuh"
 #include "pp_pillar.cuh"
@@ -75,6 +77,12 @@ struct VoxBuf {
     void *lkey;            // [Q] their first keys, same order
     int32_t *q_of_pid;     // [rows]
     u64 *coarse, *fine;    // splitters (64-bit mode): [NCHUNK-1], [NFINE-1]
+    // partitioned front end (vox_part_kernel / vox_select_kernel): cell = (local id << pt_lg) | group
+    int32_t *pt_cursor;    // [G] records appended to each group's bin
+    int32_t *pt_cell;      // [G][pt_cap] cell of the record
+    void *pt_key;          // [G][pt_cap] key of the record
+    int32_t *pt_flag;      // != 0: a bin overflowed -> the per-point kernels A / Q / C run instead
+    int32_t pt_on, pt_lg, pt_cap, pt_D;   // enabled; log2 G; bin capacity; local ids per group = ceil(cells / G)
 };
 
 // Cell index along one axis, bit-identical to the reference's floor((p - r) / v) in its promotion regime: the exact
@@ -296,6 +304,16 @@ vox_scatter_kernel(const float *__restrict__ points, int64_t n, const VoxParams 
     __shared__ CoarseTable s_ct;
     constexpr bool WIDE = sizeof(K) == 8;
     bool waited = false;
+    if (w.pt_on) {
+        // behind the partitioned front end this kernel only runs when a bin overflowed
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (__ldcg(w.pt_flag) == 0) return;
+        if (WIDE) {
+            load_coarse(s_ct, w.coarse);
+            __syncthreads();
+        }
+        waited = true;
+    }
     for (int64_t b0 = (int64_t)blockIdx.x * (VOX_THREADS * SC_IT); b0 < n; b0 += (int64_t)gridDim.x * (VOX_THREADS * SC_IT)) {
         const int64_t p0 = b0 + threadIdx.x;
         int32_t cell[SC_IT];
@@ -369,6 +387,7 @@ template <typename K>
 __global__ void __launch_bounds__(Q1_THREADS) vox_cell_prefix_kernel(const VoxParams prm, const VoxBuf w)
 {
     pdl_enter();
+    if (w.pt_on && __ldcg(w.pt_flag) == 0) return;
     const int nq = w.counters[0];
     const int lane = threadIdx.x & 31;
     const int P = prm.P;
@@ -420,6 +439,7 @@ template <typename K>
 __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, const VoxParams prm, const VoxBuf w)
 {
     pdl_enter();
+    if (w.pt_on && __ldcg(w.pt_flag) == 0) return;
     __shared__ __align__(16) uint8_t s_sat[PLACE_TABLE];
     constexpr bool WIDE = sizeof(K) == 8;
     const int nq = w.counters[0];
@@ -852,6 +872,369 @@ vox_gather_pfn_kernel(const float *__restrict__ points, const int32_t *__restric
     }
 }
 
+// ---- partitioned front end (replaces A / Q / C when every bin fits) ----------------------------------------------------
+// The per-point kernels A and C pay two dependent random L2 round trips per point.  Here the points are first
+// partitioned by cell group (group = low bits of the cell, so the cells of a dense cluster spread over the groups):
+//   P1 vox_part_kernel    per tile of 4096 points: cell, key; rank inside the tile's share of each group with shared-
+//                         memory atomics, ONE global atomic per (tile, group) to reserve bin space, records (cell, key)
+//                         written in runs
+//   P2 vox_select_kernel  one CTA per group, everything in shared memory: counting sort of the group's keys by local
+//                         cell id (direct table, ceil(cells / G) entries), then one warp per cell keeps the max_points
+//                         smallest keys, sorted: rows[q], first[q], cell_of_q[q] -- what the ranking and gather kernels read
+// A bin that overflows (a group with more than pt_cap points) raises pt_flag: P2 returns and the kernels A / Q / C,
+// which otherwise exit at once, do the frame.
+constexpr int PT_THREADS = 512, PT_IT = 8, PT_TILE = PT_THREADS * PT_IT;
+
+template <typename K>
+__global__ void __launch_bounds__(PT_THREADS)
+vox_part_kernel(const float *__restrict__ points, int64_t n, const VoxParams prm, const int32_t *__restrict__ perm,
+                const VoxBuf w)
+{
+    // PDL as in kernel A: the first tile is read and binned before the dependency wait (the init kernel orders
+    // wait -> trigger, so the producer of the points is complete)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    extern __shared__ int pt_smem[];
+    constexpr bool WIDE = sizeof(K) == 8;
+    const int G = 1 << w.pt_lg, gmask = G - 1, cap = w.pt_cap;
+    int *s_hist = pt_smem, *s_base = pt_smem + G;
+    const int tid = threadIdx.x;
+    bool waited = false;
+    for (int64_t t0 = (int64_t)blockIdx.x * PT_TILE; t0 < n; t0 += (int64_t)gridDim.x * PT_TILE) {
+        for (int g = tid; g < G; g += PT_THREADS) s_hist[g] = 0;
+        __syncthreads();
+        int32_t cell[PT_IT];
+        int r[PT_IT];
+        uint32_t prim[PT_IT];
+#pragma unroll
+        for (int k = 0; k < PT_IT; ++k) {
+            const int64_t p = t0 + k * PT_THREADS + tid;
+            cell[k] = -1;
+            prim[k] = 0u;
+            r[k] = 0;
+            if (p >= n) continue;
+            const int64_t idx = perm ? (int64_t)(uint32_t)perm[p] : p;
+            float x, y, z, refl = 0.f;
+            if (prm.vec4) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(points) + idx);
+                x = v.x; y = v.y; z = v.z; refl = v.w;
+            } else {
+                const float *pt = points + idx * prm.C;
+                x = __ldg(pt); y = __ldg(pt + 1); z = __ldg(pt + 2);
+                if (WIDE) refl = __ldg(pt + 3);
+            }
+            cell[k] = point_cell(prm, x, y, z);
+            if (WIDE) prim[k] = ~ordered_bits(refl);
+        }
+#pragma unroll
+        for (int k = 0; k < PT_IT; ++k)
+            if (cell[k] >= 0) r[k] = atomicAdd(s_hist + (cell[k] & gmask), 1);
+        if (!waited) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            waited = true;
+        }
+        __syncthreads();
+        for (int g = tid; g < G; g += PT_THREADS) {
+            const int c = s_hist[g];
+            if (c) s_base[g] = atomicAdd(w.pt_cursor + g, c);
+        }
+        __syncthreads();
+        bool over = false;
+#pragma unroll
+        for (int k = 0; k < PT_IT; ++k) {
+            if (cell[k] < 0) continue;
+            const int64_t p = t0 + k * PT_THREADS + tid;
+            const int g = cell[k] & gmask;
+            const int pos = s_base[g] + r[k];
+            if (pos >= cap) { over = true; continue; }
+            const size_t at = (size_t)g * cap + pos;
+            w.pt_cell[at] = cell[k];
+            ((K *)w.pt_key)[at] = WIDE ? (K)(((u64)prim[k] << 32) | (uint32_t)p) : (K)(uint32_t)p;
+        }
+        if (over) *w.pt_flag = 1;
+        __syncthreads();
+    }
+}
+
+template <typename K>
+__device__ __forceinline__ K shfl_idx_key(K v, int src)
+{
+    if (sizeof(K) == 8) {
+        unsigned lo = __shfl_sync(0xFFFFFFFFu, (unsigned)v, src), hi = __shfl_sync(0xFFFFFFFFu, (unsigned)((u64)v >> 32), src);
+        return (K)(((u64)hi << 32) | lo);
+    }
+    return (K)__shfl_sync(0xFFFFFFFFu, (unsigned)v, src);
+}
+
+// ascending bitonic sort of one key per lane
+template <typename K>
+__device__ __forceinline__ K warp_sort32(K k, int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            const K o = shfl_xor_key<K>(k, j);
+            const bool take_min = ((lane & size) == 0) != ((lane & j) != 0);
+            k = take_min ? (k < o ? k : o) : (k < o ? o : k);
+        }
+    }
+    return k;
+}
+
+// the 32 smallest of two ascending 32-key sequences, ascending
+template <typename K>
+__device__ __forceinline__ K warp_merge_low(K a, K b, int lane)
+{
+    const K o = shfl_idx_key<K>(b, 31 - lane);
+    K m = a < o ? a : o;                                  // bitonic
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const K x = shfl_xor_key<K>(m, j);
+        m = (lane & j) ? (m < x ? x : m) : (m < x ? m : x);
+    }
+    return m;
+}
+
+// key chunk (0 .. NCHUNK-1, monotone in the key): sample quantiles (64-bit keys) or geometric in the position
+template <typename K>
+__device__ __forceinline__ int key_chunk(const CoarseTable &t, K key, int bits)
+{
+    if (sizeof(K) == 8) return coarse_chunk(t, (uint32_t)((u64)key >> 32), (uint32_t)key);
+    return geo_bin<C_OCT, C_SUB>((uint32_t)key, bits);
+}
+
+constexpr int SEL_THREADS = 512, SEL_RPT = 16, SEL_WARPS = SEL_THREADS / 32;   // pt_cap <= SEL_THREADS * SEL_RPT
+constexpr int SEL_PEND = 64;
+
+template <typename K>
+__global__ void __launch_bounds__(SEL_THREADS, 2)
+vox_select_kernel(const VoxParams prm, const VoxBuf w)
+{
+    pdl_enter();
+    if (__ldcg(w.pt_flag) != 0) return;
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    const int cap = w.pt_cap, D = w.pt_D, lg = w.pt_lg, G = 1 << lg, P = prm.P;
+    K *s_seg = reinterpret_cast<K *>(sel_smem);                               // [cap] keys, grouped by cell
+    K *s_pend = s_seg + cap;                                                  // [SEL_WARPS][SEL_PEND]
+    int *s_off = reinterpret_cast<int *>(s_pend + SEL_WARPS * SEL_PEND);      // [D + 1] counts, then exclusive offsets
+    const int nbig_max = cap / 33 + 1;                                        // cells with more than 32 points
+    uint32_t *s_cc = reinterpret_cast<uint32_t *>(s_off + D + 1);             // [nbig_max][NCHUNK / 2] chunk counts, 16 bit
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_cc + nbig_max * (NCHUNK / 2));   // [D] occupied local ids
+    uint8_t *s_aux = reinterpret_cast<uint8_t *>(s_list + D);                 // [cap] chunk of the key at that position
+    uint8_t *s_big = s_aux + cap;                                             // [D] index of a big cell's counters
+    __shared__ int s_warp[SEL_WARPS], s_qbase, s_next, s_nbig;
+    __shared__ CoarseTable s_ct;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (D + SEL_THREADS - 1) / SEL_THREADS;                      // table entries per thread (<= 16)
+    if (sizeof(K) == 8) load_coarse(s_ct, w.coarse);                          // visible after the first barrier below
+    for (int g = blockIdx.x; g < G; g += gridDim.x) {
+        const int R = __ldcg(w.pt_cursor + g);
+        if (R == 0) continue;
+        for (int i = tid; i <= D; i += SEL_THREADS) s_off[i] = 0;
+        for (int i = tid; i < nbig_max * (NCHUNK / 2); i += SEL_THREADS) s_cc[i] = 0u;
+        if (tid == 0) s_nbig = 0;
+        __syncthreads();
+        const int32_t *gcell = w.pt_cell + (size_t)g * cap;
+        const K *gkey = (const K *)w.pt_key + (size_t)g * cap;
+        // A: count per local cell id; a record remembers (local id, arrival index)
+        uint32_t rec[SEL_RPT];
+#pragma unroll
+        for (int j = 0; j < SEL_RPT; ++j) {
+            if (j * SEL_THREADS >= R) break;              // uniform: a group rarely needs all SEL_RPT rounds
+            const int i = tid + j * SEL_THREADS;
+            rec[j] = 0;
+            if (i < R) {
+                const int l = __ldcg(gcell + i) >> lg;
+                rec[j] = ((uint32_t)l << 16) | (uint32_t)atomicAdd(s_off + l, 1);
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the counts (high half) and of the occupied flags (low half), `per` entries per thread
+        int cnt[16];
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cnt[k] = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k >= per) break;
+            const int l = tid * per + k;
+            cnt[k] = l < D ? s_off[l] : 0;
+            sum += (cnt[k] << 16) + (cnt[k] ? 1 : 0);
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int base = incl - sum, total = 0;
+#pragma unroll
+        for (int k = 0; k < SEL_WARPS; ++k) {
+            const int v = s_warp[k];
+            if (k < warp) base += v;
+            total += v;
+        }
+        const int ncell = total & 0xFFFF;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k >= per) break;
+            const int l = tid * per + k;
+            if (l < D) {
+                s_off[l] = base >> 16;
+                if (cnt[k]) s_list[base & 0xFFFF] = (uint16_t)l;
+                s_big[l] = cnt[k] > 32 ? (uint8_t)atomicAdd(&s_nbig, 1) : (uint8_t)0xFF;
+                base += (cnt[k] << 16) + (cnt[k] ? 1 : 0);
+            }
+        }
+        if (tid == 0) {
+            s_off[D] = R;
+            s_qbase = atomicAdd(w.counters, ncell);
+            s_next = 0;
+        }
+        __syncthreads();
+        // B: keys into their cell's segment; the keys of big cells (more than 32 points) are also counted per key chunk
+#pragma unroll
+        for (int j = 0; j < SEL_RPT; ++j) {
+            if (j * SEL_THREADS >= R) break;
+            const int i = tid + j * SEL_THREADS;
+            if (i < R) {
+                const int l = (int)(rec[j] >> 16);
+                const int pos = s_off[l] + (int)(rec[j] & 0xFFFFu);
+                const K key = __ldcg(gkey + i);
+                s_seg[pos] = key;
+                const int bg = s_big[l];
+                if (bg != 0xFF) {
+                    const int ch = key_chunk<K>(s_ct, key, prm.bits);
+                    s_aux[pos] = (uint8_t)ch;
+                    atomicAdd(s_cc + bg * (NCHUNK / 2) + (ch >> 1), 1u << ((ch & 1) * 16));
+                }
+            }
+        }
+        __syncthreads();
+        // C: one warp per cell (dynamic assignment).  Rows are written UNSORTED (the gather kernels sort a row in
+        // registers); what matters here is which keys are kept, and the cell's smallest key.
+        //   n <= P      every key is kept
+        //   n <= 32     one bitonic sort, the first P
+        //   else        the old algorithm, in shared memory: histogram of the cell's keys over the 64 key chunks ->
+        //               saturation chunk; keys of lower chunks are kept as they come, the r free slots go to the r
+        //               smallest keys of the saturation chunk's window (a handful of keys).  A window wider than a warp
+        //               (heavily tied or concentrated keys) falls back to a streaming top-P selection over the cell.
+        const int qbase = s_qbase;
+        K *pend = s_pend + warp * SEL_PEND;
+        for (;;) {
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&s_next, 1);
+            c = __shfl_sync(0xFFFFFFFFu, c, 0);
+            if (c >= ncell) break;
+            const int l = s_list[c];
+            const int off = s_off[l], nn = s_off[l + 1] - off;
+            const K *seg = s_seg + off;
+            const int q = qbase + c;
+            K *row = (K *)w.rows + (size_t)q * P;
+            K kmin = KeyInf<K>::value();                  // lane-local minimum of the kept keys
+            if (nn <= P) {
+                if (lane < nn) kmin = seg[lane];
+                if (lane < P) row[lane] = kmin;
+            } else if (nn <= 32) {
+                K best = lane < nn ? seg[lane] : KeyInf<K>::value();
+                best = warp_sort32<K>(best, lane);
+                if (lane < P) row[lane] = best;
+                kmin = best;
+            } else {
+                const uint32_t cw = s_cc[(int)s_big[l] * (NCHUNK / 2) + lane];
+                const int c0 = (int)(cw & 0xFFFFu), c1 = (int)(cw >> 16);
+                const uint8_t *aux = s_aux + off;
+                int incl = c0 + c1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int e0 = incl - c0 - c1, e1 = e0 + c0;          // exclusive prefixes of chunks 2*lane, 2*lane + 1
+                int sat = e1 >= P ? 2 * lane : (incl >= P ? 2 * lane + 1 : NCHUNK);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sat = min(sat, __shfl_xor_sync(0xFFFFFFFFu, sat, o));
+                const int base = __shfl_sync(0xFFFFFFFFu, (sat & 1) ? e1 : e0, sat >> 1);      // keys below the window
+                const int wn = __shfl_sync(0xFFFFFFFFu, (sat & 1) ? c1 : c0, sat >> 1);        // keys in the window
+                const int r = P - base;                                                       // 1 <= r <= wn
+                __syncwarp();
+                if (wn > 32) {
+                    K best = KeyInf<K>::value(), thr = KeyInf<K>::value();
+                    int np = 0;
+                    for (int b = 0; b < nn; b += 32) {
+                        const K k = b + lane < nn ? seg[b + lane] : KeyInf<K>::value();
+                        const bool pass = k < thr;
+                        const unsigned mask = __ballot_sync(0xFFFFFFFFu, pass);
+                        if (!mask) continue;
+                        if (pass) pend[np + __popc(mask & lanemask_lt())] = k;
+                        np += __popc(mask);
+                        if (np >= 32) {
+                            __syncwarp();
+                            K cnd = pend[lane];
+                            const K rest = pend[32 + lane];
+                            __syncwarp();
+                            np -= 32;
+                            if (lane < np) pend[lane] = rest;
+                            __syncwarp();
+                            cnd = warp_sort32<K>(cnd, lane);
+                            best = warp_merge_low<K>(best, cnd, lane);
+                            thr = shfl_idx_key<K>(best, P - 1);
+                        }
+                    }
+                    if (np > 0) {
+                        __syncwarp();
+                        K cnd = lane < np ? pend[lane] : KeyInf<K>::value();
+                        cnd = warp_sort32<K>(cnd, lane);
+                        best = warp_merge_low<K>(best, cnd, lane);
+                    }
+                    __syncwarp();
+                    if (lane < P) row[lane] = best;
+                    kmin = best;
+                } else {
+                    int nk = 0, nw = 0;
+                    for (int b = 0; b < nn; b += 32) {
+                        const bool in = b + lane < nn;
+                        const K k = in ? seg[b + lane] : KeyInf<K>::value();
+                        const int ch = in ? (int)aux[b + lane] : NCHUNK;
+                        const unsigned mk = __ballot_sync(0xFFFFFFFFu, ch < sat), mw = __ballot_sync(0xFFFFFFFFu, ch == sat);
+                        if (ch < sat) {
+                            row[nk + __popc(mk & lanemask_lt())] = k;
+                            kmin = k < kmin ? k : kmin;
+                        } else if (ch == sat) {
+                            pend[nw + __popc(mw & lanemask_lt())] = k;
+                        }
+                        nk += __popc(mk);
+                        nw += __popc(mw);
+                    }
+                    __syncwarp();
+                    // the r smallest of the window's wn keys: rank by counting
+                    const K kw = lane < wn ? pend[lane] : KeyInf<K>::value();
+                    int rank = 0;
+                    for (int j = 0; j < wn; ++j) rank += (pend[j] < kw) ? 1 : 0;
+                    if (lane < wn && rank < r) {
+                        row[base + rank] = kw;
+                        kmin = kw < kmin ? kw : kmin;
+                    }
+                    __syncwarp();
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const K x = shfl_xor_key<K>(kmin, o);
+                kmin = x < kmin ? x : kmin;
+            }
+            if (lane == 0) {
+                ((K *)w.first)[q] = kmin;
+                w.cell_of_q[q] = (l << lg) | g;
+                w.cnt[(size_t)q * NCHUNK + NCHUNK - 1] = nn;      // the gather kernels read the cell's point count here
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 int64_t max_rows_of(int64_t n, const pp_voxel_cfg *c)
 {
@@ -867,6 +1250,37 @@ struct Carve {
     InitArgs ia;
     int64_t Q;
 };
+
+// Partitioned front end: G = 2^lg groups of about <= 1024 points, ceil(cells / G) <= 8192 local cell ids per group (the
+// direct table of vox_select_kernel), bins of `cap` records (4 x the mean, at most what one CTA sorts in shared memory).
+// Everything here depends on (n, cfg) only, so the workspace size and the launch sequence agree.
+constexpr int PT_MAX_LG = 13, PT_MAX_D = 8192;
+struct PartPlan {
+    int on, lg, cap, D;
+};
+PartPlan plan_part(int64_t n, const pp_voxel_cfg *c)
+{
+    PartPlan p = {0, 0, 0, 0};
+    // Opt-in (PP_VOX_PATH=partition): measured on B200 at 1e6 points this front end is slower than the per-point
+    // kernels (P1 15 us + P2 36 us against 22 + 17 us, and 74 against 57 us per frame with 24 frames in flight), see
+    // DESIGN.md section 7; it stays as a tested alternative, not as the product path.
+    const char *path = getenv("PP_VOX_PATH");
+    if (!path || strcmp(path, "partition") != 0) return p;
+    if (c->max_points > 32 || n < 1) return p;
+    const int64_t cells = (int64_t)c->grid[0] * c->grid[1] * c->grid[2];
+    int lg = 3;
+    while (lg < PT_MAX_LG && (n >> lg) > 1024) ++lg;
+    while (lg < PT_MAX_LG && ((cells + ((int64_t)1 << lg) - 1) >> lg) > PT_MAX_D) ++lg;
+    const int64_t D = (cells + ((int64_t)1 << lg) - 1) >> lg;
+    if (D > PT_MAX_D) return p;
+    int64_t cap = 4 * ((n + ((int64_t)1 << lg) - 1) >> lg);
+    cap = (cap + 511) / 512 * 512;
+    cap = cap < 1024 ? 1024 : (cap > SEL_THREADS * SEL_RPT ? SEL_THREADS * SEL_RPT : cap);
+    const char *ecap = getenv("PP_VOX_CAP");               // tests: a small capacity forces the overflow path
+    if (ecap && atoi(ecap) > 0 && atoi(ecap) < cap) cap = atoi(ecap);
+    p.on = 1; p.lg = lg; p.cap = (int)cap; p.D = (int)D;
+    return p;
+}
 
 inline int64_t units16(size_t bytes) { return (int64_t)(align_up(bytes, 16) / 16); }
 
@@ -888,6 +1302,10 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
     r.b.counters = a.take<int32_t>(64);
     r.b.hist = a.take<int32_t>(NBIN);
     r.b.fill = a.take<int32_t>(16);
+    const PartPlan pl = plan_part(n, c);
+    r.b.pt_on = pl.on; r.b.pt_lg = pl.lg; r.b.pt_cap = pl.cap; r.b.pt_D = pl.D;
+    r.b.pt_flag = r.b.counters + 16;
+    r.b.pt_cursor = a.take<int32_t>(pl.on ? ((size_t)1 << pl.lg) : 4);      // zeroed with the counters
     const size_t z0_off = (size_t)((char *)r.b.counters - (char *)ws), z0_bytes = a.off - z0_off;
     r.b.base = a.take<int32_t>(NFINE + 1);
     r.b.cell_of_q = a.take<int32_t>((size_t)r.Q);
@@ -905,6 +1323,9 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
     r.b.q_of_pid = a.take<int32_t>((size_t)max_rows_of(n, c));
     r.b.coarse = a.take<u64>(NCHUNK);
     r.b.fine = a.take<u64>(NFINE);
+    const size_t recs = pl.on ? ((size_t)pl.cap << pl.lg) : 4;
+    r.b.pt_cell = a.take<int32_t>(recs);
+    r.b.pt_key = a.take<char>(recs * ksz);
     *total = align_up(a.off);
     // every array starts 256-byte aligned, so rounding the fills up to 16 bytes stays inside the padding
     r.ia.ff_ptr[0] = (int4 *)r.b.map;    r.ia.ff_n[0] = units16(ff0_bytes);
@@ -938,6 +1359,28 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
         PP_CUDA_TRY(cudaGetDevice(&dev));
         PP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         sc_resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+    }
+    if (w.pt_on) {
+        const int G = 1 << w.pt_lg;
+        const size_t p1_smem = (size_t)2 * G * sizeof(int);
+        const size_t p2_smem = ((size_t)w.pt_cap + SEL_WARPS * SEL_PEND) * sizeof(K) + ((size_t)w.pt_D + 1) * sizeof(int) +
+                               (size_t)(w.pt_cap / 33 + 1) * (NCHUNK / 2) * sizeof(uint32_t) + (size_t)w.pt_D * sizeof(uint16_t) +
+                               (size_t)w.pt_cap + (size_t)w.pt_D + 16;
+        static size_t p1_set = 48 * 1024, p2_set = 48 * 1024;
+        if (p1_smem > p1_set) {
+            PP_CUDA_TRY(cudaFuncSetAttribute(vox_part_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem));
+            p1_set = p1_smem;
+        }
+        if (p2_smem > p2_set) {
+            PP_CUDA_TRY(cudaFuncSetAttribute(vox_select_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem));
+            p2_set = p2_smem;
+        }
+        const int64_t tiles = ceil_div(n, PT_TILE);
+        launch_pdl(vox_part_kernel<K>, dim3((unsigned)(tiles < 148 * 2 ? tiles : 148 * 2)), dim3(PT_THREADS), p1_smem, st, points,
+                   n, prm, perm, w);
+        if (int rc = check_launch("vox_part_kernel")) return rc;
+        launch_pdl(vox_select_kernel<K>, dim3((unsigned)(G < 148 * 4 ? G : 148 * 4)), dim3(SEL_THREADS), p2_smem, st, prm, w);
+        if (int rc = check_launch("vox_select_kernel")) return rc;
     }
     const int64_t sc_blocks = ceil_div(n, VOX_THREADS * SC_IT);
     launch_pdl(vox_scatter_kernel<K>, dim3((unsigned)(sc_blocks < sc_resident ? sc_blocks : sc_resident)), dim3(VOX_THREADS), 0, st,

@@ -99,6 +99,58 @@ def test_voxelize_full_size_vs_oracle(pp, oracle, kind, n, cap, P):
     assert (m >= 1).all() and (m <= P).all()
 
 
+@pytest.fixture(params=["partitioned", "points", "overflow"])
+def vox_front_end(request, monkeypatch):
+    """The three ways a frame can go through the voxelizer's front end: the per-point kernels (the product path),
+    partitioned by cell group (opt-in, PP_VOX_PATH=partition, max_points <= 32), and partitioned with a bin overflow
+    that hands the frame back to the per-point kernels on the device (PP_VOX_CAP forces a tiny bin)."""
+    if request.param != "points":
+        monkeypatch.setenv("PP_VOX_PATH", "partition")
+    if request.param == "overflow":
+        monkeypatch.setenv("PP_VOX_CAP", "40")
+    return request.param
+
+
+@pytest.mark.parametrize("case", ["dense300k", "uniform300k_break", "one_cell", "two_points_per_cell", "P5", "tiny"])
+def test_voxelize_front_ends_vs_oracle(pp, oracle, vox_front_end, case):
+    from objectdetection_3d_b200 import synth
+    g = synth.G_KITTI
+    vs = np.array(g["voxel_size"], dtype=np.float32)
+    rg = np.array(g["point_cloud_range"], dtype=np.float64)
+    P, cap = 32, 12000
+    rng = np.random.default_rng(11)
+    if case == "dense300k":
+        pts = synth.dense_tile(n=300_000, seed=21)
+    elif case == "uniform300k_break":
+        pts = synth.uniform_tile(n=300_000, margin=0.02)          # ~160k occupied cells >> cap: the `break`
+    elif case == "one_cell":
+        pts = np.empty((50_000, 4), np.float32)                  # every point in one pillar (one bin takes them all)
+        pts[:, 0] = 10.0 + 0.05 * rng.random(50_000)
+        pts[:, 1] = 0.05 * rng.random(50_000)
+        pts[:, 2] = -1.0
+        pts[:, 3] = rng.permutation(50_000) / 50_000
+    elif case == "two_points_per_cell":
+        pts = synth.uniform_tile(n=20_000, margin=0.02)
+        pts = np.concatenate([pts, pts + np.float32(1e-3)]).astype(np.float32)
+        pts[:, 3] = rng.permutation(len(pts)) / len(pts)
+        cap = 100_000
+    elif case == "P5":
+        pts = synth.dense_tile(n=100_000, seed=22, n_cells=900, n_clusters=40)
+        P = 5
+    else:
+        pts = synth.dense_tile(n=700, seed=23, n_cells=30, n_clusters=3)
+    n = len(pts)
+    for refl in (True, False):
+        if refl:
+            v, c, m = pp.ops_numba.points_to_voxel(pts.copy(), vs, rg, P, cap, True)
+            ov, oc, om = oracle.points_to_voxel(pts, vs, rg, P, cap, True)
+        else:
+            perm = rng.permutation(n).astype(np.int32)
+            v, c, m = pp.ops_numba.points_to_voxel(pts.copy(), vs, rg, P, cap, False, perm=perm)
+            ov, oc, om = oracle.points_to_voxel(pts, vs, rg, P, cap, False, perm=perm)
+        assert np.array_equal(c, oc) and np.array_equal(m, om) and np.array_equal(v, ov), (case, refl, vox_front_end)
+
+
 def test_voxelize_edge_cases(pp):
     from objectdetection_3d_b200 import synth
     g = synth.G_KITTI
