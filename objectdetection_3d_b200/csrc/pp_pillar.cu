@@ -288,25 +288,29 @@ constexpr int CV_CGROUPS = 4;      // channel groups (blockIdx.y): channel c bel
 // griddepcontrol.wait, i.e. while the (FP32-bound) PFN kernel is still running; after the wait only the columns that
 // hold a pillar (a few percent) are overwritten with features.
 __global__ void __launch_bounds__(CV_THREADS, 6)
-scatter_canvas_wave_kernel(const float *__restrict__ feat, const int32_t *__restrict__ map, int C, int D, int64_t HW,
-                           int64_t total_cols, float *__restrict__ canvas)
+scatter_canvas_wave_kernel(const float *__restrict__ feat, const int32_t *__restrict__ map, int C, int D, int HW,
+                           float *__restrict__ canvas)
 {
+    // grid = (column tiles of one plane, channel groups, planes): no index divisions (64-bit divisions by run-time
+    // values were half of this kernel's instructions)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int64_t col = (int64_t)blockIdx.x * CV_THREADS + threadIdx.x;
+    const int col = blockIdx.x * CV_THREADS + threadIdx.x;                // float4 column inside the plane
     const int cq = blockIdx.y;
-    const int64_t hw4 = HW >> 2;
-    const int64_t plane = col / hw4, cell = (col - plane * hw4) << 2;     // plane = b * D + z
-    const int64_t b = plane / D, z = plane - b * D;
-    const int64_t chan_stride = (int64_t)D * HW;
-    float *dst0 = canvas + (b * C * D + z) * HW + cell + (int64_t)cq * chan_stride;
-    if (col < total_cols) {
+    const int plane = blockIdx.z;                                         // b * D + z
+    const int b = plane / D, z = plane - b * D;
+    const int cell = col << 2;
+    const size_t chan_stride = (size_t)D * HW;
+    float *dst0 = canvas + ((size_t)b * C * D + z) * HW + cell + (size_t)cq * chan_stride;
+    const bool in = cell < HW;
+    if (in) {
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
         float *dst = dst0;
+#pragma unroll 4
         for (int c = cq; c < C; c += CV_CGROUPS, dst += CV_CGROUPS * chan_stride) *reinterpret_cast<float4 *>(dst) = zero;
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (col >= total_cols) return;
-    const int4 pid = *reinterpret_cast<const int4 *>(map + plane * HW + cell);
+    if (!in) return;
+    const int4 pid = *reinterpret_cast<const int4 *>(map + (size_t)plane * HW + cell);
     if ((pid.x & pid.y & pid.z & pid.w) < 0) return;      // all four cells empty (the common case)
     float *dst = dst0;
     for (int c = cq; c < C; c += CV_CGROUPS, dst += CV_CGROUPS * chan_stride) {
@@ -330,7 +334,7 @@ int fill_pillar_in(PillarIn &a, const float *voxels, const float *in, const void
     return 0;
 }
 
-dim3 canvas_wave_grid(int64_t total_cols) { return dim3((unsigned)ceil_div(total_cols, CV_THREADS), CV_CGROUPS); }
+dim3 canvas_wave_grid(int64_t HW, int64_t planes) { return dim3((unsigned)ceil_div(HW / 4, CV_THREADS), CV_CGROUPS, (unsigned)planes); }
 
 unsigned pillar_grid(int64_t M)
 {
@@ -460,9 +464,8 @@ extern "C" int pp_scatter_dense(const float *feat, const void *coors, int coors_
     }
     const unsigned grid = (unsigned)((int64_t)B * D * tiles_per_plane);
     const bool vec4 = (HW % 4 == 0) && ((uintptr_t)canvas % 16 == 0);
-    if (vec4 && ((uintptr_t)map % 16 == 0))
-        scatter_canvas_wave_kernel<<<canvas_wave_grid((int64_t)B * D * (HW / 4)), CV_THREADS, 0, st>>>(
-            feat, map, C, D, HW, (int64_t)B * D * (HW / 4), canvas);
+    if (vec4 && ((uintptr_t)map % 16 == 0) && HW < (1ll << 30) && (int64_t)B * D < 65536)
+        scatter_canvas_wave_kernel<<<canvas_wave_grid(HW, (int64_t)B * D), CV_THREADS, 0, st>>>(feat, map, C, D, (int)HW, canvas);
     else if (vec4)
         scatter_canvas_kernel<true><<<grid, CANVAS_WARPS * 32, 0, st>>>(feat, map, C, D, HW, (int)tiles_per_plane, canvas);
     else
@@ -482,9 +485,9 @@ extern "C" int pp_scatter_mapped(const float *feat, const int32_t *pillar_map, i
     PP_REQUIRE((int64_t)B * D * tiles_per_plane < (1ll << 31), "canvas too large");
     const unsigned grid = (unsigned)((int64_t)B * D * tiles_per_plane);
     const bool vec4 = (HW % 4 == 0) && ((uintptr_t)canvas % 16 == 0);
-    if (vec4 && ((uintptr_t)pillar_map % 16 == 0))
-        launch_pdl(scatter_canvas_wave_kernel, canvas_wave_grid((int64_t)B * D * (HW / 4)), dim3(CV_THREADS), 0, st, feat,
-                   pillar_map, C, D, HW, (int64_t)B * D * (HW / 4), canvas);
+    if (vec4 && ((uintptr_t)pillar_map % 16 == 0) && HW < (1ll << 30) && (int64_t)B * D < 65536)
+        launch_pdl(scatter_canvas_wave_kernel, canvas_wave_grid(HW, (int64_t)B * D), dim3(CV_THREADS), 0, st, feat, pillar_map, C, D,
+                   (int)HW, canvas);
     else if (vec4)
         launch_pdl(scatter_canvas_kernel<true>, dim3(grid), dim3(CANVAS_WARPS * 32), 0, st, feat, pillar_map, C, D, HW,
                    (int)tiles_per_plane, canvas);
