@@ -30,7 +30,12 @@ NMS_SCORE_THR = 0.0      # every one of the 20k boxes is a candidate (scores are
 NMS_IOU_THR = 0.1
 NMS_EXTENT = 40.0        # dense case of SURVEY.md 8(d) NMS20k
 RING_TILES = 24          # distinct input tiles per GPU  (24 x 16 MB), one per frame slot
-RING_CANVAS = 24         # distinct output canvases      (12 x 54.9 MB) -> working set > 126 MB L2
+RING_CANVAS = 24         # distinct output canvases      (24 x 54.9 MB) -> working set > 126 MB L2
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture of this workload
+# (profiles/r01_ncu_frame_full_v6.md); cold-cache, one launch
+NCU_TRAFFIC = {"vox_scatter_kernel": 18.99e6, "vox_place_kernel": 13.48e6, "vox_gather_pfn_kernel": 19.60e6,
+               "scatter_canvas_kernel": 8.04e6, "vox_rank_kernel": 0.20e6, "vox_init_kernel": 0.15e6,
+               "vox_cell_prefix_kernel": 2.95e6}
 WORKLOAD = "D1M tile (1e6 pts, 0.16 m pillars, 12000x32, 432x496 canvas, reflectance order) + NMS20k dense"
 
 
@@ -45,10 +50,10 @@ def parse():
     return ap.parse_args()
 
 
-def base_config(n_gpus):
+def base_config(n_gpus, slots=RING_TILES):
     return {"workload": WORKLOAD, "n_points": N_POINTS, "n_boxes": N_BOXES, "frames_per_step_per_gpu": 1,
             "nms": {"score_thr": NMS_SCORE_THR, "iou_thr": NMS_IOU_THR, "extent_m": NMS_EXTENT},
-            "parallelism": "frames sharded over %d GPU(s), no collective; 12 independent frames in flight per GPU, one CUDA graph per frame" % n_gpus,
+            "parallelism": "frames sharded over %d GPU(s), no collective; %d independent frames in flight per GPU, one CUDA graph per frame slot" % (n_gpus, slots),
             "l2": "inputs larger than L2: ring of %d tiles + %d canvases per GPU (%.0f MB)" %
                   (RING_TILES, RING_CANVAS, RING_TILES * 16.0 + RING_CANVAS * 54.85)}
 
@@ -455,13 +460,13 @@ def run_ours(args):
         per_launch_b = kbytes.get(dom, 0)
         ach = per_launch_b / (kern[dom]["avg_us"] * 1e-6) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": 18.98e6 if dom == "vox_scatter_kernel" else None,
+                    "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC.get(dom),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_b,
                     "avg_launch_us": kern[dom]["avg_us"],
                     "share_of_step": kern[dom]["ms_per_step"] / max(sum(v["ms_per_step"] for v in kern.values()), 1e-9),
                     "how": "CUDA events on the launching stream around every launch (pp_profile_*), separate single-"
                            "stream pass of %d steps after the timed region; traffic = dram read+write of one "
-                           "ncu --set full capture (profiles/r01_ncu_frame_full_v3.md)" % prof_steps}
+                           "ncu --set full capture (profiles/r01_ncu_frame_full_v6.md)" % prof_steps}
     stage_roof = {
         "voxelize": {"algorithmic_MB": vox_b / 1e6, "us": 1e3 * t_vox, "GBps": vox_b / (t_vox * 1e-3) / 1e9,
                      "frac": vox_b / (t_vox * 1e-3) / 1e9 / hbm_peak},
@@ -483,7 +488,7 @@ def run_ours(args):
             "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "frames_in_flight": N_SLOTS, "single_stream_ms_per_frame": ms_serial / min(K, 100),
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(base_config(world), pillars=m_pillars, nms_kept=keep_n),
+            "config": dict(base_config(world, N_SLOTS), pillars=m_pillars, nms_kept=keep_n),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K,

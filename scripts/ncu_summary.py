@@ -15,11 +15,11 @@ def g(r, k, d=0.0):
 units = rows[1]
 def unit(k):
     return units[ix[k]] if k in ix else ""
-print("| kernel | grid x block | regs | us | DRAM rd MB | DRAM wr MB | DRAM GB/s | L2 sectors M | FP32 pipe % | issue % | warps active % |")
-print("|---|---|---|---|---|---|---|---|---|---|---|")
+print("| kernel | grid x block | regs | us | DRAM rd MB | DRAM wr MB | DRAM GB/s | L2 sectors M | FP32 pipe % | warp instr M | IPC / SM | warps active % |")
+print("|---|---|---|---|---|---|---|---|---|---|---|---|")
 for r in rows[2:]:
     name = r[ix["Kernel Name"]]
-    short = re.sub(r"^.*?::", "", re.sub(r"\(.*$", "", name)).replace("unnamed>::", "")
+    short = re.sub(r"^.*?::", "", re.sub(r"\(.*$", "", name)).replace("unnamed>::", "").lstrip("<")
     if rx and not rx.search(name):
         continue
     us = g(r, "gpu__time_duration.sum")
@@ -31,7 +31,8 @@ for r in rows[2:]:
         if v == "rd": rd *= f
         else: wr *= f
     fp32 = g(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", g(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"))
-    print("| %s | %d x %d | %d | %.2f | %.2f | %.2f | %.0f | %.2f | %.1f | %.1f | %.1f |" % (
+    print("| %s | %d x %d | %d | %.2f | %.2f | %.2f | %.0f | %.2f | %.1f | %.2f | %.2f | %.1f |" % (
         short[:44], g(r, "launch__grid_size"), g(r, "launch__block_size"), g(r, "launch__registers_per_thread"), us, rd, wr,
         (rd + wr) / us * 1e3 if us else 0, g(r, "lts__t_sectors.sum") / 1e6, fp32,
-        g(r, "smsp__issue_active.avg.pct"), g(r, "sm__warps_active.avg.pct_of_peak_sustained_active")))
+        g(r, "smsp__inst_executed.sum") / 1e6, g(r, "sm__inst_executed.avg.per_cycle_active"),
+        g(r, "sm__warps_active.avg.pct_of_peak_sustained_active")))
