@@ -767,6 +767,25 @@ __device__ __forceinline__ K shfl_xor_key(K v, int m)
     return (K)__shfl_xor_sync(0xFFFFFFFFu, (unsigned)v, m);
 }
 
+template <typename K>
+__device__ __forceinline__ K shfl_down_key(K v, int d)
+{
+    if (sizeof(K) == 8) {
+        unsigned lo = __shfl_down_sync(0xFFFFFFFFu, (unsigned)v, d), hi = __shfl_down_sync(0xFFFFFFFFu, (unsigned)((u64)v >> 32), d);
+        return (K)(((u64)hi << 32) | lo);
+    }
+    return (K)__shfl_down_sync(0xFFFFFFFFu, (unsigned)v, d);
+}
+template <typename K>
+__device__ __forceinline__ K shfl_up_key(K v, int d)
+{
+    if (sizeof(K) == 8) {
+        unsigned lo = __shfl_up_sync(0xFFFFFFFFu, (unsigned)v, d), hi = __shfl_up_sync(0xFFFFFFFFu, (unsigned)((u64)v >> 32), d);
+        return (K)(((u64)hi << 32) | lo);
+    }
+    return (K)__shfl_up_sync(0xFFFFFFFFu, (unsigned)v, d);
+}
+
 template <typename K, bool TWO>
 __global__ void __launch_bounds__(VOX_THREADS)
 vox_gather_sorted_kernel(const float *__restrict__ points, const int32_t *__restrict__ perm, const VoxBuf w,
@@ -876,13 +895,30 @@ vox_gather_pfn_kernel(const float *__restrict__ points, const int32_t *__restric
         const int nk = total < P ? total : P;
         K k0 = lane < nk ? krow[lane] : KeyInf<K>::value();
         if (!(k0 < cutoff)) k0 = KeyInf<K>::value();
+        // The placement leaves a row sorted up to the order inside a key-chunk window (a few keys in arrival order), so
+        // a few odd-even transposition rounds finish it; the bitonic network (15 steps) is the fallback for rows that
+        // are not nearly sorted.
+        bool sorted = false;
+#pragma unroll 1
+        for (int round = 0; round < 5; ++round) {
+            const K nx = shfl_down_key<K>(k0, 1);
+            sorted = __ballot_sync(0xFFFFFFFFu, lane < 31 && nx < k0) == 0u;
+            if (sorted) break;
+            const K o = shfl_xor_key<K>(k0, 1);                       // pairs (0,1) (2,3) ...
+            k0 = (lane & 1) ? (k0 < o ? o : k0) : (k0 < o ? k0 : o);
+            const K up = shfl_down_key<K>(k0, 1), dn = shfl_up_key<K>(k0, 1);      // pairs (1,2) (3,4) ...
+            if (lane & 1) { if (lane < 31) k0 = k0 < up ? k0 : up; }
+            else if (lane > 0) k0 = k0 < dn ? dn : k0;
+        }
+        if (!sorted) {
 #pragma unroll
-        for (int size = 2; size <= 32; size <<= 1) {
+            for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
-            for (int j = size >> 1; j > 0; j >>= 1) {
-                const K o = shfl_xor_key<K>(k0, j);
-                const bool take_min = ((lane & size) == 0) != ((lane & j) != 0);
-                k0 = take_min ? (k0 < o ? k0 : o) : (k0 < o ? o : k0);
+                for (int j = size >> 1; j > 0; j >>= 1) {
+                    const K o = shfl_xor_key<K>(k0, j);
+                    const bool take_min = ((lane & size) == 0) != ((lane & j) != 0);
+                    k0 = take_min ? (k0 < o ? k0 : o) : (k0 < o ? o : k0);
+                }
             }
         }
         const bool valid = k0 != KeyInf<K>::value();
