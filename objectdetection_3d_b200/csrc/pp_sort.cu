@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 sort_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int pass,
                  const uint32_t *__restrict__ hist /* this pass: [256] */, uint32_t *status /* [tiles][256] */,
-                 uint32_t *ticket)
+                 uint32_t *ticket, bool direct)
 {
     constexpr int TILE = SORT_THREADS * ITEMS;
     __shared__ uint32_t warp_hist[SORT_WARPS][RADIX + 1];
@@ -94,6 +94,23 @@ sort_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restric
         uint32_t excl = 0;
         if (tile == 0) {
             atomicExch(my, FLAG_PREFIX | tile_count);
+        } else if (direct) {
+            // few tiles (the NMS sizes): every tile publishes its own count at once and sums the counts of ALL its
+            // predecessors with independent loads -- one L2 round trip instead of a chain of up to `tile` dependent ones
+            atomicExch(my, FLAG_AGG | tile_count);
+            for (int t0 = 0; t0 < (int)tile; t0 += 8) {
+                uint32_t sv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    sv[j] = 1u << 30;        // "published, count 0" for slots past the last predecessor
+                    if (t0 + j < (int)tile) sv[j] = *((volatile uint32_t *)(status + (size_t)(t0 + j) * RADIX + d));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    while ((sv[j] & FLAG_MASK) == 0) sv[j] = *((volatile uint32_t *)(status + (size_t)(t0 + j) * RADIX + d));
+                    excl += sv[j] & VAL_MASK;
+                }
+            }
         } else {
             atomicExch(my, FLAG_AGG | tile_count);
             int64_t t = (int64_t)tile - 1;
@@ -299,7 +316,8 @@ int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *k
         uint32_t *kout = (p & 1) ? keys_out : s.keys_tmp;
         uint32_t *vout = (p & 1) ? vals_out : s.vals_tmp;
         sort_pass_kernel<SORT_ITEMS><<<s.tiles, SORT_THREADS, 0, st>>>(
-            kin, vin, kout, vout, n, p, s.hist + p * RADIX, s.status + (size_t)p * s.tiles * RADIX, s.tickets + p);
+            kin, vin, kout, vout, n, p, s.hist + p * RADIX, s.status + (size_t)p * s.tiles * RADIX, s.tickets + p,
+            s.tiles <= 32);
         if (int rc = check_launch("sort_pass_kernel")) return rc;
         kin = kout;
         vin = vout;
