@@ -323,7 +323,9 @@ __device__ __forceinline__ int coarse_chunk(const CoarseTable &t, uint32_t prim,
     return lo;
 }
 
-constexpr int SC_IT = 4;      // points per thread and iteration: their dependent chains (map -> counter) are interleaved
+constexpr int SC_IT = 1;      // points per thread and iteration.  Measured with the rows pre-claimed (kernel A0), 24 frames in
+                              // flight: 8 / 4 / 2 / 1 points give 57.5 / 53.0 / 51.9 / 51.5 us per frame and 31 / 25 / 22 / 20 us alone;
+                              // more warps hide the map -> counter round trips better than interleaved chains of one thread
 
 template <typename K>
 __global__ void __launch_bounds__(VOX_THREADS)
@@ -460,8 +462,17 @@ __global__ void __launch_bounds__(Q1_THREADS) vox_cell_prefix_kernel(const VoxPa
     }
 }
 
+template <int N> __device__ __forceinline__ bool any_active(const bool (&a)[N])
+{
+    bool r = false;
+#pragma unroll
+    for (int k = 0; k < N; ++k) r = r || a[k];
+    return r;
+}
+
 // ---- C: per point, slot inside the pillar ------------------------------------------------------------------------
 constexpr int PLACE_THREADS = 512;
+constexpr int PLACE_IT = 2;                 // points per thread and iteration
 constexpr int PLACE_TABLE = 40 * 1024;      // cells whose saturation chunk is cached in shared memory
 
 // Persistent CTAs: the per-cell saturation chunk (1 byte per cell) is staged in shared memory once per CTA, so the
@@ -480,10 +491,11 @@ __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, con
         reinterpret_cast<uint4 *>(s_sat)[i] = reinterpret_cast<const uint4 *>(w.sat_of_q)[i];
     __syncthreads();
     const int P = prm.P;
-    // Four points per thread and iteration: their loads, and later their insertion chains, are issued back to back
+    // PLACE_IT points per thread and iteration (2: 20.2 us against 24.5 with 4 and 20.9 with 1): their loads, and later
+    // their insertion chains, are issued back to back
     // (an in-order warp stalls at the first use of a result, so one point at a time would serialise every L2 round
     // trip of the chain).  The scatter kernel left (row, primary key) and (chunk, ticket) per point.
-    constexpr int IT = 4;
+    constexpr int IT = PLACE_IT;
     const int64_t stride = (int64_t)gridDim.x * PLACE_THREADS;
     for (int64_t p0 = (int64_t)blockIdx.x * PLACE_THREADS + threadIdx.x; p0 < n; p0 += stride * IT) {
         int q[IT], tk[IT];
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(PLACE_THREADS) vox_place_kernel(int64_t n, con
         }
         // A few points share a window: sorted insertion with a lock-free atomicMin chain.  Slots only decrease and
         // every displaced key is pushed one slot down, so the final window is sorted for any interleaving.
-        while (act[0] || act[1] || act[2] || act[3]) {
+        while (any_active(act)) {
             K old[IT];
 #pragma unroll
             for (int k = 0; k < IT; ++k)
@@ -1465,7 +1477,7 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
     if (int rc = check_launch("vox_cell_prefix_kernel")) return rc;
     const int place_per_sm = 4;
     {
-        const int64_t want = ceil_div(n, PLACE_THREADS * 4), cap_p = 148 * place_per_sm;
+        const int64_t want = ceil_div(n, PLACE_THREADS * PLACE_IT), cap_p = 148 * place_per_sm;
         launch_pdl(vox_place_kernel<K>, dim3((unsigned)(want < cap_p ? want : cap_p)), dim3(PLACE_THREADS), 0, st, n, prm, w);
     }
     if (int rc = check_launch("vox_place_kernel")) return rc;
