@@ -32,10 +32,16 @@ NMS_EXTENT = 40.0        # dense case of SURVEY.md 8(d) NMS20k
 RING_TILES = 24          # distinct input tiles per GPU  (24 x 16 MB), one per frame slot
 RING_CANVAS = 24         # distinct output canvases      (24 x 54.9 MB) -> working set > 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture of this workload
-# (profiles/r01_ncu_frame_full_v7.md); cold-cache, one launch
-NCU_TRAFFIC = {"vox_scatter_kernel": 18.92e6, "vox_place_kernel": 13.48e6, "vox_gather_pfn_kernel": 19.61e6,
-               "scatter_canvas_kernel": 8.43e6, "vox_rank_kernel": 0.20e6, "vox_init_kernel": 0.15e6,
+# (profiles/r01_ncu_frame_full_v8.md); cold-cache, one launch
+NCU_TRAFFIC = {"vox_scatter_kernel": 18.90e6, "vox_place_kernel": 13.47e6, "vox_gather_pfn_kernel": 19.61e6,
+               "scatter_canvas_kernel": 7.24e6, "vox_rank_kernel": 0.20e6, "vox_init_kernel": 0.15e6,
                "vox_preclaim_kernel": 8.37e6, "vox_cell_prefix_kernel": 2.95e6}
+# what the same capture says limits each kernel of the HBM path (none of them is limited by DRAM bandwidth)
+NCU_LIMITER = {"vox_gather_pfn_kernel": "FP32 pipe 33 % (6.3 M FFMA of the PFN, its arithmetic minimum) + gather latency; DRAM 0.75 TB/s",
+               "vox_scatter_kernel": "two dependent random L2 accesses per point (cell map -> chunk counter); DRAM 0.9 TB/s",
+               "vox_place_kernel": "dependent random L2 accesses (per-point record -> cell prefix -> row slot); DRAM 0.65 TB/s",
+               "vox_rank_kernel": "two grid barriers + cooperative launch; no DRAM traffic",
+               "scatter_canvas_kernel": "store path (lg_throttle): 54.9 MB at 3.3 TB/s, memset of the same buffer 5.3 TB/s"}
 WORKLOAD = "D1M tile (1e6 pts, 0.16 m pillars, 12000x32, 432x496 canvas, reflectance order) + NMS20k dense"
 
 
@@ -460,13 +466,13 @@ def run_ours(args):
         per_launch_b = kbytes.get(dom, 0)
         ach = per_launch_b / (kern[dom]["avg_us"] * 1e-6) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC.get(dom),
+                    "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC.get(dom), "limiter": NCU_LIMITER.get(dom),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_b,
                     "avg_launch_us": kern[dom]["avg_us"],
                     "share_of_step": kern[dom]["ms_per_step"] / max(sum(v["ms_per_step"] for v in kern.values()), 1e-9),
                     "how": "CUDA events on the launching stream around every launch (pp_profile_*), separate single-"
                            "stream pass of %d steps after the timed region; traffic = dram read+write of one "
-                           "ncu --set full capture (profiles/r01_ncu_frame_full_v7.md)" % prof_steps}
+                           "ncu --set full capture (profiles/r01_ncu_frame_full_v8.md)" % prof_steps}
     stage_roof = {
         "voxelize": {"algorithmic_MB": vox_b / 1e6, "us": 1e3 * t_vox, "GBps": vox_b / (t_vox * 1e-3) / 1e9,
                      "frac": vox_b / (t_vox * 1e-3) / 1e9 / hbm_peak},
