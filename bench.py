@@ -184,6 +184,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(torch, local):
+    """Run this rank on the CPUs of its GPU's NUMA node, so that the pinned host buffers it first-touches (and the
+    threads that feed them) sit next to the GPU's PCIe root: at 8 ranks the host side of the copies is the limit."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        dev = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % dev).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except (OSError, ValueError, AttributeError):
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -195,6 +217,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(torch, local)
     if world > 1:
         # NCCL prints its version banner on stdout; keep stdout for the one JSON line
         sys.stdout.flush()
@@ -494,7 +517,7 @@ def run_ours(args):
             "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "frames_in_flight": N_SLOTS, "single_stream_ms_per_frame": ms_serial / min(K, 100),
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(base_config(world, N_SLOTS), pillars=m_pillars, nms_kept=keep_n),
+            "config": dict(base_config(world, N_SLOTS), pillars=m_pillars, nms_kept=keep_n, host_numa_node=numa),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K,
