@@ -884,7 +884,7 @@ struct PfnArgs {
 constexpr int GP_THREADS = 128;      // 4 pillars per CTA
 
 template <typename K>
-__global__ void __launch_bounds__(GP_THREADS, 6)
+__global__ void __launch_bounds__(GP_THREADS, 8)
 vox_gather_pfn_kernel(const float *__restrict__ points, const int32_t *__restrict__ perm, const VoxBuf w,
                       const int32_t *__restrict__ voxel_num, int P, float *__restrict__ voxels,
                       int32_t *__restrict__ num_points, const PfnArgs pa)
@@ -1510,7 +1510,7 @@ int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *per
     const bool vec4 = prm.vec4 && ((uintptr_t)voxels % 16 == 0);
     if (pfn) {
         const int64_t want = ceil_div(max_rows, GP_THREADS / 32);
-        launch_pdl(vox_gather_pfn_kernel<K>, dim3((unsigned)(want < 148 * 6 ? want : 148 * 6)), dim3(GP_THREADS), 0, st, points,
+        launch_pdl(vox_gather_pfn_kernel<K>, dim3((unsigned)(want < 148 * 8 ? want : 148 * 8)), dim3(GP_THREADS), 0, st, points,
                    perm, w, (const int32_t *)voxel_num, prm.P, voxels, num_points, *pfn);
         return check_launch("vox_gather_pfn_kernel");
     }
