@@ -169,7 +169,7 @@ pfn_kernel(const PillarIn a, const float *__restrict__ W, const float *__restric
 // Fast path of the fused single-layer PillarFeatureNet (Cin <= 12, U <= 64, P <= 32): the two weight rows a lane owns
 // live in registers for the whole grid-stride loop; the per-pillar work is pfn_pillar (pp_pillar.cuh).
 template <int CIN>
-__global__ void __launch_bounds__(PIL_THREADS, 6)
+__global__ void __launch_bounds__(PIL_THREADS, 8)
 pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const float *__restrict__ scale,
                        const float *__restrict__ shift, int U, float *__restrict__ out)
 {
