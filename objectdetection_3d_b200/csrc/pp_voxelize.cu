@@ -328,7 +328,7 @@ constexpr int SC_IT = 1;      // points per thread and iteration.  Measured with
                               // more warps hide the map -> counter round trips better than interleaved chains of one thread
 
 template <typename K>
-__global__ void __launch_bounds__(VOX_THREADS)
+__global__ void __launch_bounds__(VOX_THREADS, 8)
 vox_scatter_kernel(const float *__restrict__ points, int64_t n, const VoxParams prm, const int32_t *__restrict__ perm,
                    const VoxBuf w)
 {
