@@ -287,7 +287,7 @@ constexpr int CV_CGROUPS = 4;      // channel groups (blockIdx.y): channel c bel
 // PDL: the zeros do not depend on anything the predecessors on the stream compute, so they are written BEFORE
 // griddepcontrol.wait, i.e. while the (FP32-bound) PFN kernel is still running; after the wait only the columns that
 // hold a pillar (a few percent) are overwritten with features.
-__global__ void __launch_bounds__(CV_THREADS, 6)
+__global__ void __launch_bounds__(CV_THREADS, 8)
 scatter_canvas_wave_kernel(const float *__restrict__ feat, const int32_t *__restrict__ map, int C, int D, int HW,
                            float *__restrict__ canvas)
 {
