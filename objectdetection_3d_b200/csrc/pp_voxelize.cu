@@ -952,15 +952,19 @@ vox_gather_pfn_kernel(const float *__restrict__ points, const int32_t *__restric
     }
 }
 
-// ---- partitioned front end (replaces A / Q / C when every bin fits) ----------------------------------------------------
+// ---- partitioned front end, OPT-IN (PP_VOX_PATH=partition; replaces A0 / A / Q / C when every bin fits) ----------------
+// Measured slower than the per-point kernels on B200 and therefore not the product path; it is
+// bit-exact and covered by the front-end tests.
 // The per-point kernels A and C pay two dependent random L2 round trips per point.  Here the points are first
 // partitioned by cell group (group = low bits of the cell, so the cells of a dense cluster spread over the groups):
 //   P1 vox_part_kernel    per tile of 4096 points: cell, key; rank inside the tile's share of each group with shared-
 //                         memory atomics, ONE global atomic per (tile, group) to reserve bin space, records (cell, key)
 //                         written in runs
 //   P2 vox_select_kernel  one CTA per group, everything in shared memory: counting sort of the group's keys by local
-//                         cell id (direct table, ceil(cells / G) entries), then one warp per cell keeps the max_points
-//                         smallest keys, sorted: rows[q], first[q], cell_of_q[q] -- what the ranking and gather kernels read
+//                         cell id (direct table, ceil(cells / G) entries; the keys of cells with more than 32 points are
+//                         also counted per key chunk), then one warp per cell keeps the max_points smallest keys
+//                         (unsorted: the gather kernels sort a row): rows[q], first[q], cell_of_q[q] -- what the
+//                         ranking and gather kernels read
 // A bin that overflows (a group with more than pt_cap points) raises pt_flag: P2 returns and the kernels A / Q / C,
 // which otherwise exit at once, do the frame.
 constexpr int PT_THREADS = 512, PT_IT = 8, PT_TILE = PT_THREADS * PT_IT;
