@@ -115,6 +115,22 @@ PP_API int pp_voxelize_features(const float *points, int64_t n_points, const pp_
                          int32_t *voxel_num, int32_t *pillar_map, const pp_pfn_fused *pfn, void *workspace,
                          size_t workspace_bytes, pp_stream_t stream);
 
+/*
+ * The whole of stages 1 + 2 of one frame in one call: pp_voxelize_features AND the dense scatter of the pillar
+ * features into the BEV pseudo-image.  Replaces PointPillarsVoxelization.forward (model/PointPillars.py:330-354) +
+ * PillarFeatureNet.forward (:480-526) + SparseConvTensor(...).dense().view (:565-571) for batch size 1.
+ * canvas: (1, (units+1)*D, H, W) float32 of THIS frame (for a batch pass each frame's slice), written completely:
+ * the gather kernel stores each pillar's features straight from its registers (channel c of cell (z,y,x) at
+ * canvas[(c*D+z)*H*W + y*W + x]); the zeros of all other cells are written by the per-point kernels before their
+ * dependency waits, i.e. off the critical path.  canvas must be 32-byte aligned, (units+1)*D*H*W a multiple of 8.
+ * pfn->feat (rows, units+1) and pillar_map may be NULL here (they are by-products, not inputs of the scatter).
+ * Same restrictions as pp_voxelize_features.
+ */
+PP_API int pp_voxelize_scatter(const float *points, int64_t n_points, const pp_voxel_cfg *cfg, int order,
+                        const int32_t *perm, float *voxels, int32_t *coors, int32_t *num_points,
+                        int32_t *voxel_num, int32_t *pillar_map, const pp_pfn_fused *pfn, float *canvas,
+                        void *workspace, size_t workspace_bytes, pp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Stage 2 -- pillar decoration, PFN and dense scatter.
  * ---------------------------------------------------------------------------------------- */

@@ -40,6 +40,8 @@ SIGNATURES = {
     "pp_voxelize": (ctypes.c_int, [_vp, _i64, _cfgp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pp_voxelize_features": (ctypes.c_int, [_vp, _i64, _cfgp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                             _vp]),
+    "pp_voxelize_scatter": (ctypes.c_int, [_vp, _i64, _cfgp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                           _vp]),
     "pp_decorate": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _i64, _vp, ctypes.c_int, ctypes.c_int,
                                    _f32, _f32, _f32, _f32, _vp, _vp]),
     "pp_pfn_layer": (ctypes.c_int, [_vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int,

@@ -166,20 +166,22 @@ pfn_kernel(const PillarIn a, const float *__restrict__ W, const float *__restric
     }
 }
 
-// Fast path of the fused single-layer PillarFeatureNet (Cin <= 12, U <= 64, P <= 32): the two weight rows a lane owns
-// live in registers for the whole grid-stride loop; the per-pillar work is pfn_pillar (pp_pillar.cuh).
-template <int CIN>
+// Fast path of the fused single-layer PillarFeatureNet (C <= 7, U <= 64, P <= 32): the folded weights of the two units a
+// lane owns live in registers for the whole grid-stride loop; the per-pillar work is pfn_pillar_c (pp_pillar.cuh).
+template <int C>
 __global__ void __launch_bounds__(PIL_THREADS, 8)
 pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const float *__restrict__ scale,
                        const float *__restrict__ shift, int U, float *__restrict__ out)
 {
-    pdl_enter();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(16) float smem[];
+    constexpr int LD = C <= 4 ? 4 : 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int P = a.P, C = a.C;
-    float *row = smem + warp * 32 * PFN_LDI;
-    PfnWeights<CIN> pw;
-    pfn_load_weights<CIN>(pw, W, scale, shift, U, lane);
+    const int P = a.P;
+    float *row = smem + warp * 32 * LD;
+    PfnWeightsC<C> pw;
+    pfn_load_weights_c<C>(pw, W, scale, shift, U, lane);          // weights do not depend on the predecessor
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int64_t M = a.M;
     if (a.m_dev) { int64_t md = *a.m_dev; M = md < M ? md : M; }
     const int out_w = U + 1;
@@ -188,21 +190,20 @@ pfn_fused_small_kernel(const PillarIn a, const float *__restrict__ W, const floa
         const int n = load_num(a, m);
         int cx, cy;
         load_xy(a, m, cx, cy);
-        float f[PFN_LDI];
+        float f[C];
 #pragma unroll
-        for (int k = 0; k < PFN_LDI; ++k) f[k] = 0.f;
+        for (int k = 0; k < C; ++k) f[k] = 0.f;
         if (lane < P) {
             const float *v = a.voxels + (m * P + lane) * C;
-            if (vec4) {
+            if (C == 4 && vec4) {
                 const float4 t = __ldg(reinterpret_cast<const float4 *>(v));
-                f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+                f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3 % C] = t.w;
             } else {
 #pragma unroll
-                for (int k = 0; k < PFN_LDI - 5; ++k)
-                    if (k < C) f[k] = __ldg(v + k);
+                for (int k = 0; k < C; ++k) f[k] = __ldg(v + k);
             }
         }
-        pfn_pillar<CIN>(pw, f, C, P, n, cx, cy, a.vx, a.vy, a.x_off, a.y_off, row, out + m * out_w, U, lane);
+        pfn_pillar_c<C>(pw, f, P, n, cx, cy, a.vx, a.vy, a.x_off, a.y_off, row, out + m * out_w, nullptr, 0, U, lane);
     }
 }
 
@@ -412,18 +413,18 @@ extern "C" int pp_pillar_features(const float *voxels, const void *num_points, i
     PillarIn a;
     fill_pillar_in(a, voxels, nullptr, num_points, num_kind, coors, coors_kind, M, m_dev, P, C, C + 5, vx, vy, x_off,
                    y_off);
-    if (C + 5 <= PFN_LDI && U <= 64 && P <= 32) {
-        size_t smem = (size_t)PIL_WARPS * 32 * PFN_LDI * sizeof(float);
+    if (C <= 7 && U <= 64 && P <= 32) {
+        size_t smem = (size_t)PIL_WARPS * 32 * (C <= 4 ? 4 : 8) * sizeof(float);
         int64_t want = ceil_div(M, PIL_WARPS);
         // one resident wave that leaves room on every SM for the canvas kernel's early (pre-wait) zero fill
         const unsigned grid = (unsigned)(want < 148 * 6 ? (want > 0 ? want : 1) : 148 * 6);
         cudaStream_t st = (cudaStream_t)stream;
-        switch (C + 5) {
-        case 8: launch_pdl(pfn_fused_small_kernel<8>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
-        case 9: launch_pdl(pfn_fused_small_kernel<9>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
-        case 10: launch_pdl(pfn_fused_small_kernel<10>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
-        case 11: launch_pdl(pfn_fused_small_kernel<11>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
-        default: launch_pdl(pfn_fused_small_kernel<12>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
+        switch (C) {
+        case 3: launch_pdl(pfn_fused_small_kernel<3>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
+        case 4: launch_pdl(pfn_fused_small_kernel<4>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
+        case 5: launch_pdl(pfn_fused_small_kernel<5>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
+        case 6: launch_pdl(pfn_fused_small_kernel<6>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
+        default: launch_pdl(pfn_fused_small_kernel<7>, dim3(grid), dim3(PIL_THREADS), smem, st, a, weight, scale, shift, U, feat); break;
         }
         return check_launch("pfn_fused_small_kernel");
     }

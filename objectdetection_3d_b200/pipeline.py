@@ -85,13 +85,28 @@ class FramePipeline:
             _ptr(self.num), _ptr(self.voxel_num), _ptr(self.pillar_map), ctypes.byref(self.pfn_args), _ptr(self.vox_ws),
             self.vox_ws_bytes, _sp(stream)))
 
+    def voxelize_scatter(self, points, canvas, stream):
+        """The frame in one call: voxelize + PillarFeatureNet + dense scatter (pp_voxelize_scatter)."""
+        n = points.shape[0]
+        assert self.fused and n <= self.n_points and points.shape[1] == self.C
+        assert canvas.is_contiguous() and canvas.numel() == (self.U + 1) * self.D * self.H * self.W
+        _lib.check(self.lib.pp_voxelize_scatter(
+            _ptr(points), n, ctypes.byref(self.cfg), self.order, None, _ptr(self.voxels), _ptr(self.coors),
+            _ptr(self.num), _ptr(self.voxel_num), None, ctypes.byref(self.pfn_args), _ptr(canvas), _ptr(self.vox_ws),
+            self.vox_ws_bytes, _sp(stream)))
+
     def scatter(self, canvas, stream):
         _lib.check(self.lib.pp_scatter_mapped(_ptr(self.feat), _ptr(self.pillar_map), self.U + 1, 1, self.D, self.H,
                                               self.W, _ptr(canvas), _sp(stream)))
 
     def run(self, points, canvas, stream=None, fused=None):
+        """fused: None / True = one call (pp_voxelize_scatter) when the shapes allow it; "features" = gather fused with the
+        PFN + the stand-alone canvas kernel; False = the three stand-alone calls."""
         stream = stream or torch.cuda.current_stream()
-        if self.fused if fused is None else fused:
+        mode = (True if self.fused else False) if fused is None else fused
+        if mode is True and canvas.data_ptr() % 32 == 0 and canvas.numel() % 8 == 0:
+            self.voxelize_scatter(points, canvas, stream)
+        elif mode:
             self.voxelize_features(points, stream)
             self.scatter(canvas, stream)
         else:

@@ -20,7 +20,7 @@ def once():
     if what == "vox":
         pipe.voxelize(pts, st)
     if what in ("enc", "frame"):
-        pipe.run(pts, canvas, st, fused=("unfused" not in sys.argv))
+        pipe.run(pts, canvas, st, fused=(False if "unfused" in sys.argv else ("features" if "features" in sys.argv else True)))
     if what in ("nms", "frame"):
         nms.run(b, s, 0.0, 0.1, 0, st)
 

@@ -99,20 +99,12 @@ def test_voxelize_full_size_vs_oracle(pp, oracle, kind, n, cap, P):
     assert (m >= 1).all() and (m <= P).all()
 
 
-@pytest.fixture(params=["partitioned", "points", "overflow"])
-def vox_front_end(request, monkeypatch):
-    """The three ways a frame can go through the voxelizer's front end: the per-point kernels (the product path),
-    partitioned by cell group (opt-in, PP_VOX_PATH=partition, max_points <= 32), and partitioned with a bin overflow
-    that hands the frame back to the per-point kernels on the device (PP_VOX_CAP forces a tiny bin)."""
-    if request.param != "points":
-        monkeypatch.setenv("PP_VOX_PATH", "partition")
-    if request.param == "overflow":
-        monkeypatch.setenv("PP_VOX_CAP", "40")
-    return request.param
-
-
-@pytest.mark.parametrize("case", ["dense300k", "uniform300k_break", "one_cell", "two_points_per_cell", "P5", "tiny"])
-def test_voxelize_front_ends_vs_oracle(pp, oracle, vox_front_end, case):
+@pytest.mark.parametrize("case", ["dense300k", "uniform300k_break", "dense50k_hash", "uniform60k_break_hash", "one_cell",
+                                  "two_points_per_cell", "P5", "P50", "P100", "tiny"])
+def test_voxelize_addressing_vs_oracle(pp, oracle, case):
+    """Both ways a cell is addressed (slot = cell when the grid is no larger than the 2n-slot hash table would be, else
+    the hash of the cell id: KITTI grid with n <= 65 536 points), every selection width (max_points <= 32, <= 64, any),
+    a cell that holds every point, and the `break` at max_voxels."""
     from objectdetection_3d_b200 import synth
     g = synth.G_KITTI
     vs = np.array(g["voxel_size"], dtype=np.float32)
@@ -123,8 +115,13 @@ def test_voxelize_front_ends_vs_oracle(pp, oracle, vox_front_end, case):
         pts = synth.dense_tile(n=300_000, seed=21)
     elif case == "uniform300k_break":
         pts = synth.uniform_tile(n=300_000, margin=0.02)          # ~160k occupied cells >> cap: the `break`
+    elif case == "dense50k_hash":
+        pts = synth.dense_tile(n=50_000, seed=24, n_cells=2500, n_clusters=60)
+    elif case == "uniform60k_break_hash":
+        pts = synth.uniform_tile(n=60_000, margin=0.02)
+        cap = 5000
     elif case == "one_cell":
-        pts = np.empty((50_000, 4), np.float32)                  # every point in one pillar (one bin takes them all)
+        pts = np.empty((50_000, 4), np.float32)                  # every point in one pillar
         pts[:, 0] = 10.0 + 0.05 * rng.random(50_000)
         pts[:, 1] = 0.05 * rng.random(50_000)
         pts[:, 2] = -1.0
@@ -134,9 +131,9 @@ def test_voxelize_front_ends_vs_oracle(pp, oracle, vox_front_end, case):
         pts = np.concatenate([pts, pts + np.float32(1e-3)]).astype(np.float32)
         pts[:, 3] = rng.permutation(len(pts)) / len(pts)
         cap = 100_000
-    elif case == "P5":
+    elif case in ("P5", "P50", "P100"):
         pts = synth.dense_tile(n=100_000, seed=22, n_cells=900, n_clusters=40)
-        P = 5
+        P = int(case[1:])
     else:
         pts = synth.dense_tile(n=700, seed=23, n_cells=30, n_clusters=3)
     n = len(pts)
@@ -148,7 +145,27 @@ def test_voxelize_front_ends_vs_oracle(pp, oracle, vox_front_end, case):
             perm = rng.permutation(n).astype(np.int32)
             v, c, m = pp.ops_numba.points_to_voxel(pts.copy(), vs, rg, P, cap, False, perm=perm)
             ov, oc, om = oracle.points_to_voxel(pts, vs, rg, P, cap, False, perm=perm)
-        assert np.array_equal(c, oc) and np.array_equal(m, om) and np.array_equal(v, ov), (case, refl, vox_front_end)
+        assert np.array_equal(c, oc) and np.array_equal(m, om) and np.array_equal(v, ov), (case, refl)
+
+
+def test_voxelize_ties_full_size(pp, oracle):
+    """D1M-ties at full size: reflectance quantised to 256 levels (as real LiDAR intensity is).  The reference's order
+    among equal reflectances is numba's quicksort order: replayed through PP_ORDER_PERM it is bit-exact; the default
+    path follows the documented rule (reflectance desc, index asc; -0.0 == +0.0)."""
+    from objectdetection_3d_b200 import synth
+    g = synth.G_KITTI
+    vs = np.array(g["voxel_size"], dtype=np.float32)
+    rg = np.array(g["point_cloud_range"], dtype=np.float64)
+    pts = synth.dense_tile(n=1_000_000, seed=2025, ties=True)
+    pts[::7919, 3] = -0.0                                          # a negative zero ties with the positive ones
+    perm = oracle.numba_argsort_desc(pts[:, 3])
+    v, c, m = pp.ops_numba.points_to_voxel(pts.copy(), vs, rg, 32, 12000, True, perm=perm)
+    ov, oc, om = oracle.points_to_voxel(pts, vs, rg, 32, 12000, True)
+    assert np.array_equal(c, oc) and np.array_equal(m, om) and np.array_equal(v, ov)
+    v, c, m = pp.ops_numba.points_to_voxel(pts.copy(), vs, rg, 32, 12000, True)
+    stable = np.argsort(-pts[:, 3], kind="stable")
+    ov, oc, om = oracle.points_to_voxel(pts, vs, rg, 32, 12000, False, perm=stable)
+    assert np.array_equal(c, oc) and np.array_equal(m, om) and np.array_equal(v.view(np.uint32), ov.view(np.uint32))
 
 
 def test_voxelize_edge_cases(pp):
@@ -415,13 +432,16 @@ def test_head_box3d_assign_runs(pp):
 
 @pytest.mark.parametrize("order", ["reflectance", "given"])
 def test_frame_pipeline_full_size(pp, oracle, order):
-    """BASELINE configs[1] through the preallocated pipeline (voxelize -> PFN -> mapped scatter) vs the oracle."""
+    """BASELINE configs[1] through the preallocated pipeline vs the oracle: the one-call frame (pp_voxelize_scatter), the
+    gather+PFN kernel with the stand-alone canvas kernel, and the three stand-alone calls give bit-identical frames."""
     from objectdetection_3d_b200 import _lib, pipeline, synth
     g, pfn = synth.G_KITTI, synth.pfn_params(9, 63, seed=5)
     pts = synth.dense_tile()
     pipe = pipeline.FramePipeline(g, pfn, len(pts),
                                   order=_lib.ORDER_REFLECTANCE_DESC if order == "reflectance" else _lib.ORDER_GIVEN)
+    assert pipe.fused
     canvas = pipe.new_canvas()
+    canvas.fill_(7.0)           # every element of the canvas must be written by the call
     for _ in range(2):          # twice: the workspace must be reusable without re-initialisation by the caller
         pipe.run(cu(pts), canvas)
     torch.cuda.synchronize()
@@ -431,20 +451,21 @@ def test_frame_pipeline_full_size(pp, oracle, order):
     assert m == len(ov)
     assert np.array_equal(pipe.voxels[:m].cpu().numpy(), ov)
     assert np.array_equal(pipe.coors[:m].cpu().numpy(), oc) and np.array_equal(pipe.num[:m].cpu().numpy(), on)
-    pm = pipe.pillar_map.cpu().numpy()
-    assert (pm >= 0).sum() == m and np.array_equal(pm[oc[:, 2], oc[:, 1], oc[:, 0]], np.arange(m))
     coors4 = np.concatenate([np.zeros((m, 1), np.int64), oc[:, [2, 1, 0]].astype(np.int64)], 1)
     feat = oracle.pillar_feature_net(ov, on, coors4, [pfn], g["voxel_size"], g["point_cloud_range"])
     ref = oracle.scatter_dense(feat, coors4.astype(np.int32), 1, 1, pipe.H, pipe.W)
     got = canvas.cpu().numpy()
     scale = float(np.abs(pts[:, :3]).max())
-    assert_close_t1(got, ref, atol=1e-5 * scale * 4, what="canvas")
-    # the fused gather + PFN kernel (default) and the two separate kernels give bit-identical frames
+    assert_close_t1(pipe.feat[:m].cpu().numpy(), feat, atol=1e-6 * scale, what="features")
+    assert_close_t1(got, ref, atol=1e-6 * scale, what="canvas")
     feat_fused, vox_fused = pipe.feat[:m].clone(), pipe.voxels[:m].clone()
-    canvas2 = pipe.new_canvas()
-    assert pipe.fused
-    pipe.run(cu(pts), canvas2, fused=False)
-    torch.cuda.synchronize()
-    assert torch.equal(pipe.feat[:m], feat_fused) and torch.equal(pipe.voxels[:m], vox_fused)
-    assert torch.equal(canvas2, canvas)
+    for mode in ("features", False):
+        canvas2 = pipe.new_canvas()
+        canvas2.fill_(-3.0)
+        pipe.run(cu(pts), canvas2, fused=mode)
+        torch.cuda.synchronize()
+        assert torch.equal(pipe.feat[:m], feat_fused) and torch.equal(pipe.voxels[:m], vox_fused), mode
+        assert torch.equal(canvas2, canvas), mode
+        pm = pipe.pillar_map.cpu().numpy()
+        assert (pm >= 0).sum() == m and np.array_equal(pm[oc[:, 2], oc[:, 1], oc[:, 0]], np.arange(m))
     assert np.array_equal(got == 0, ref == 0) or np.abs(got[(got == 0) != (ref == 0)]).max() < 1e-4
