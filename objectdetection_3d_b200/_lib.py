@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpp_b200.so")
+LIB_PATH = os.environ.get("PP_B200_LIB") or os.path.join(_HERE, "libpp_b200.so")      # (override: development builds)
 
 PP_OK, PP_ERR_INVALID, PP_ERR_CUDA, PP_ERR_WORKSPACE = 0, -1, -2, -3
 ORDER_GIVEN, ORDER_REFLECTANCE_DESC, ORDER_PERM = 0, 1, 2

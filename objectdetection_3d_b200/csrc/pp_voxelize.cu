@@ -12,29 +12,32 @@
 //   slot        = rank of the key inside its cell, capped at max_points.
 //
 // A cell keeps its max_points smallest keys.  Keys are binned into 8 chunks that are monotone in K and geometric in the
-// key's quantile ([0,1/128) [1/128,1/64) ... [1/2,1]; quantiles of a sorted key sample, or of the position), so a cell
+// key's quantile ([0,1/128) [1/128,1/64) ... [1/2,1]; quantiles of a small key sample, or of the position), so a cell
 // with any number of points finds its max_points-th key in a chunk whose prefix is at most about 2 x max_points.
 // Cells are addressed directly (slot = cell) when the grid is small, through an open-addressing hash of the cell id
 // otherwise (3-D grids with millions of cells); everything after the slot lookup is the same.
 //
-// Kernels (all with programmatic dependent launch; each point costs ONE random L2 atomic per per-point pass):
+// Kernels (all with programmatic dependent launch):
 //   S  vox_init_kernel     zero the chunk counters / small counters / histogram, -1 into the hash keys and the
-//                          pillar map; reflectance order: one CTA sorts a 1024-key sample -> 7 chunk splitters + 1023
-//                          fine splitters (ranking bins)
-//   A  vox_count_kernel    per point: cell -> slot, chunk(K); cnt[slot][chunk]++ (no return value: a reduction);
-//                          per-point record (slot, chunk, key high word)
-//   B  vox_cells_kernel    per slot: counts -> saturation chunk, m = points in the chunks up to it; segment of m keys
-//                          and compact cell id q allocated with one atomic per CTA
-//   C  vox_place_kernel    per point: dropped when its chunk lies after the cell's saturation chunk (most points of a
-//                          dense cell: one cached read); else seg[cursor[slot]++] = K
-//   F  vox_first_kernel    per cell (8 lanes): first[q] = smallest key of the segment; ranking bin of it (fine
-//                          splitters + adaptive linear sub-bins) and arrival index inside the bin
-//   R  vox_bucket_kernel   every CTA scans the bin histogram in shared memory; cells in bucket order; the last CTA to
-//                          finish settles the cutoff when more than max_voxels cells are occupied
+//                          pillar map; reflectance order: 7 chunk splitters from a 128-key sample (ranked by counting)
+//   A  vox_count_kernel    per point: cell -> slot, chunk(K); ticket = cnt[slot][chunk]++ : the ONE random L2 atomic a
+//                          point costs; per-point record (slot, chunk, ticket, key high word)
+//   B  vox_cells_kernel    per slot: counts -> saturation chunk (the first chunk at which the cell holds max_points
+//                          points), m = points in the chunks up to it; segment of m keys and compact cell id q from
+//                          CTA-wide prefix sums + one atomic per CTA; the counters become write positions
+//                          (segment offset + exclusive prefix over the chunks; "dropped" after the saturation chunk)
+//   C  vox_place_kernel    per point: seg[position[slot][chunk] + ticket] = K -- one cached read and one store, no
+//                          atomic; most points of a dense cell are dropped after the read.  Segments come out ordered
+//                          by chunk.  One extra CTA sorts a 1024-key sample -> 1023 fine splitters (ranking bins)
+//   H  vox_rank_kernel     per cell (thread): smallest key = minimum over the segment's first chunk; ranking bin of
+//                          it (fine splitters + adaptive linear sub-bins), arrival index inside the bin.  The last
+//                          CTA to finish scans the bin histogram, puts the cells in bucket order and settles the
+//                          cutoff when more than max_voxels cells are occupied
 //   D  vox_gather_kernel   per cell (warp): pillar id = bucket base + smaller keys inside the bucket; the max_points
-//                          smallest keys of the segment, sorted (bitonic merges in registers), keys >= cutoff dropped;
-//                          voxels[pid][s] = points[key.index], coors, num_points, cell -> pillar map; with the fused
-//                          PillarFeatureNet the warp runs the pillar through decorate + Linear + BN + ReLU + max
+//                          smallest keys of the segment in order (ranks by counting in shared memory; bitonic merges
+//                          for long segments), keys >= cutoff dropped; voxels[pid][s] = points[key.index], coors,
+//                          num_points, cell -> pillar map; with the fused PillarFeatureNet the warp runs the pillar
+//                          through decorate + Linear + BN + ReLU + max and writes the BEV canvas column
 // Everything but the 16 B/point read and the output write is L2-resident workspace traffic.
 #include <math_constants.h>
 #include <stdlib.h>
@@ -49,11 +52,21 @@ namespace {
 typedef unsigned long long u64;
 constexpr int VOX_THREADS = 256;
 constexpr int NCH = 8;              // key chunks per cell: one 32-byte sector of counters
-constexpr int NFINE = 1024;         // sample intervals used to rank the cells' first keys
-constexpr int NSUB = 8;             // bins per sample interval on average
-constexpr int NBIN = NFINE * NSUB;  // ranking bins
-constexpr int SAMPLE = 1024;        // keys sampled for the quantile splitters (one per sorting thread)
+constexpr int NFINE = 512;          // sample intervals used to rank the cells' first keys
+constexpr int NBIN = 8192;          // ranking bins
+constexpr int SAMPLE = 512;         // keys sampled for the fine splitters
+constexpr int CSAMPLE = 128;        // keys sampled for the chunk splitters
+constexpr uint32_t DROPPED = 0xFFFFFFFFu;
 enum { CTR_NQ = 0, CTR_SEG = 1, CTR_DONE = 2 };
+
+// Development only (-DPP_TIMING): first-start / last-end %globaltimer of every kernel of a call in counters[16 ...]
+#ifdef PP_TIMING
+#define PP_T0(cnt, k) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMax((unsigned long long *)((cnt) + 16) + (k), ~t_); } } while (0)
+#define PP_T1(cnt, k) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMax((unsigned long long *)((cnt) + 16) + (k), t_); } } while (0)
+#else
+#define PP_T0(cnt, k) do { } while (0)
+#define PP_T1(cnt, k) do { } while (0)
+#endif
 
 template <typename K> struct KeyInf;
 template <> struct KeyInf<uint32_t> { static __device__ __host__ constexpr uint32_t value() { return 0xFFFFFFFFu; } };
@@ -73,62 +86,64 @@ struct VoxBuf {
     int32_t T;             // slots: the cells (direct) or a power of two >= 2 n (hash)
     int32_t hash_bits;     // 0: slot = cell
     int32_t *slot_key;     // [T] hash mode: cell of the slot, -1 empty
-    uint32_t *cnt;         // [T][NCH] chunk counts; after kernel B: [0] segment cursor, [1] saturation chunk
+    uint32_t *cnt;         // [T][NCH] chunk counts; after kernel B: write position of each chunk, DROPPED after the saturation chunk
     int32_t *counters;     // CTR_*
-    uint32_t *rec;         // [N] (slot << 3) | chunk, ~0 outside the grid      (32-bit keys)
-    uint2 *rec2;           // [N] the same + the key's high word                (64-bit keys)
-    void *seg;             // [N] keys grouped by cell
-    int4 *qinfo;           // [Q] cell, segment offset, m, points in the cell
+    uint32_t *rec_slot;    // [N] (slot << 3) | chunk, ~0 outside the grid
+    uint32_t *rec_tick;    // [N] arrival index inside (cell, chunk)
+    uint32_t *rec_hi;      // [N] key high word (64-bit keys)
+    void *seg;             // [N] keys grouped by cell, inside a cell by chunk
+    int4 *qinfo;           // [Q] cell, segment offset, m, keys in the cell's first occupied chunk
+    int4 *qxyz;            // [Q] x, y, z of the cell
     void *first;           // [Q] smallest key of the cell
     int32_t *bin_of_q;     // [Q]
-    int32_t *arr_of_q;     // [Q] arrival index inside the bin
     int32_t *hist;         // [NBIN]
     int32_t *base;         // [NBIN + 1] exclusive scan of hist
-    void *lkey;            // [Q] first keys in bucket order
-    int32_t *lq;           // [Q] their cells q
+    int32_t *arr_of_q;     // [Q] arrival index inside the bin
+    void *lkey;            // [Q] first keys in bucket order (bin by bin, arrival order inside a bin)
     void *cutoff;          // key
     u64 *coarse, *fine;    // splitters (64-bit keys): [NCH - 1], [NFINE - 1]
 };
 
 // Cell index along one axis, bit-identical to the reference's floor((p - r) / v) in its promotion regime: the exact
 // evaluation (fp64 / IEEE-fp32 division), used for points within a guard band of a cell boundary.
-__device__ __forceinline__ bool axis_cell_exact(const VoxParams &q, int j, float p, int &c)
+// (scalar arguments and not inlined: the rare path must not make the parameter block addressable or bloat the kernel)
+__device__ __noinline__ int axis_cell_exact(int regime, double r, double v, float rf, float vf, int g, float p)
 {
     double cd;
-    if (q.regime == 2) cd = floor(((double)p - q.r[j]) / q.v[j]);
-    else if (q.regime == 1) cd = floor((double)__fsub_rn(p, q.rf[j]) / q.v[j]);
-    else cd = (double)floorf(__fdiv_rn(__fsub_rn(p, q.rf[j]), q.vf[j]));
-    if (!(cd >= 0.0) || cd >= (double)q.g[j]) return false;   // also rejects NaN
-    c = (int)cd;
-    return true;
+    if (regime == 2) cd = floor(((double)p - r) / v);
+    else if (regime == 1) cd = floor((double)__fsub_rn(p, rf) / v);
+    else cd = (double)floorf(__fdiv_rn(__fsub_rn(p, rf), vf));
+    if (!(cd >= 0.0) || cd >= (double)g) return -1;           // also rejects NaN
+    return (int)cd;
 }
 
 // Linear cell of a point, or -1 outside the grid.  An fp32 reciprocal-multiply estimate decides every point that is
 // not within a guard band of a cell boundary on any axis (the band covers the rounding of r, 1/v and the two fp32
-// operations; outside it both floors agree); only those points take the exact path.  One branch per point.
+// operations; outside it the estimate's floor and the reference's agree); only those points take the exact path.
+// Six instructions per axis on the common path: subtract, multiply, round, distance to the nearest integer, band, compare.
 __device__ __forceinline__ int32_t point_cell(const VoxParams &q, float x, float y, float z)
 {
     const float p[3] = {x, y, z};
-    float fl[3];
+    int c[3];
     bool near = false, inside = true;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const float est = (p[j] - q.rf[j]) * q.inv_vf[j];
-        fl[j] = floorf(est);
-        const float fr = est - fl[j];
+        const float dist = fabsf(est - rintf(est));                // distance to the nearest cell boundary
         const float band = 1e-6f * (fabsf(est) + q.rv_abs[j]) + 1e-6f;
-        near = near || !(fr > band && fr < 1.0f - band);          // also true for NaN / huge values
-        inside = inside && (fl[j] >= 0.f) && (fl[j] < (float)q.g[j]);
+        near = near || !(dist > band);                             // also true for NaN / inf
+        c[j] = __float2int_rd(est);
+        inside = inside && ((unsigned)c[j] < (unsigned)q.g[j]);
     }
-    int cx, cy, cz;
     if (near) {
-        if (!(axis_cell_exact(q, 0, x, cx) && axis_cell_exact(q, 1, y, cy) && axis_cell_exact(q, 2, z, cz))) return -1;
-    } else {
-        if (!inside) return -1;
-        cx = (int)fl[0]; cy = (int)fl[1]; cz = (int)fl[2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) c[j] = axis_cell_exact(q.regime, q.r[j], q.v[j], q.rf[j], q.vf[j], q.g[j], p[j]);
+        if ((c[0] | c[1] | c[2]) < 0) return -1;
+    } else if (!inside) {
+        return -1;
     }
     // cell linearisation (z*gy + y)*gx + x = the (D,H,W) order of the BEV canvas
-    return (cz * q.g[1] + cy) * q.g[0] + cx;
+    return (c[2] * q.g[1] + c[1]) * q.g[0] + c[0];
 }
 
 // High word of a reflectance key: descending reflectance in ascending unsigned order; -0.0 orders like +0.0 (the
@@ -154,98 +169,82 @@ __device__ __forceinline__ int geo_bin(uint32_t u, int bits)
 }
 
 constexpr int C_OCT = 8, C_SUB = 0;      // 8 chunks: binary-geometric in the position
-constexpr int F_OCT = 8, F_SUB = 10;     // 8192 ranking bins (32-bit keys): 8 octaves x 1024 (cell minima crowd at low positions)
 
-// The same geometric chunk layout expressed as quantiles of the sorted sample: index of the lower edge of chunk b >= 1
-__device__ __forceinline__ int chunk_sample_index(int b) { return SAMPLE >> (NCH - b); }      // 8 16 32 ... 512
+// rank += (a < b) as compare + predicated increment (three instructions for a 64-bit key)
+__device__ __forceinline__ void count_if_less(int &rank, u64 a, u64 b)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.u64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(rank) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void count_if_less(int &rank, uint32_t a, uint32_t b)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(rank) : "r"(a), "r"(b));
+}
+
+__device__ __forceinline__ u64 sample_key(const float *__restrict__ points, int64_t n, int C, int i, int nsample)
+{
+    // evenly spaced sample; short inputs are padded with +inf keys
+    const int64_t idx = (n >= nsample) ? (int64_t)i * (n / nsample) : i;
+    return idx < n ? (((u64)refl_key_hi(points[idx * C + 3]) << 32) | (uint32_t)idx) : ~0ull - (u64)(nsample - i);   // (distinct pads)
+}
 
 // ---- canvas zero fill, spread over the per-point kernels ---------------------------------------------------------------
 // The fused frame call (pp_voxelize_scatter) writes the BEV canvas from the gather kernel; the zeros of the other ~95 % of
-// the canvas do not depend on anything, so slices of them are written by kernels A, C and F BEFORE their dependency wait,
+// the canvas do not depend on anything, so halves of them are written by kernels A and C BEFORE their dependency wait,
 // i.e. while the predecessor is still running: linear 256-bit stores (STG.256), fire and forget.  The init kernel
 // orders wait -> trigger, so none of this starts before the caller's earlier work on the stream is complete.
 struct FillArgs {
     float *base;          // nullptr: nothing to fill
     int64_t units;        // 32-byte units in the canvas
 };
-constexpr int FILL_SLICES = 3;
+constexpr int FILL_SLICES = 2;
 
-__device__ __forceinline__ void fill_slice(const FillArgs &fa, int slice)
+// (CTA `block` of `nblocks` taking part)
+__device__ __forceinline__ void fill_slice(const FillArgs &fa, int slice, int block, int nblocks)
 {
     if (!fa.base) return;
     const int64_t per = (fa.units + FILL_SLICES - 1) / FILL_SLICES;
     const int64_t lo = per * slice, hi = lo + per < fa.units ? lo + per : fa.units;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride)
+    const int64_t stride = (int64_t)nblocks * blockDim.x;
+    for (int64_t i = lo + (int64_t)block * blockDim.x + threadIdx.x; i < hi; i += stride)
         asm volatile("st.global.v8.f32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(fa.base + i * 8), "f"(0.f) : "memory");
 }
 
-// ---- S: workspace initialisation, and (reflectance order) quantile splitters from a key sample ----------------
-// One launch replaces the memsets: CTA 0 sorts the key sample (bitonic, shared memory) while the other CTAs fill.
+// ---- S: workspace initialisation, and (reflectance order) chunk splitters from a key sample ---------------------------
+// One launch replaces the memsets.  CTA 0 also ranks a 128-key sample by counting (no sort, no barrier chain) and
+// publishes the keys of rank 1, 2, 4 ... 64 as the starts of chunks 1 ... 7.
 struct InitArgs {
     int4 *ff_ptr[3];  int64_t ff_n[3];     // regions filled with 0xFF (16-byte units)
     int4 *z_ptr[2];   int64_t z_n[2];      // regions filled with 0
 };
 
 __global__ void __launch_bounds__(1024)
-vox_init_kernel(const float *__restrict__ points, int64_t n, int C, int wide, u64 *__restrict__ coarse,
-                u64 *__restrict__ fine, const InitArgs ia)
+vox_init_kernel(const float *__restrict__ points, int64_t n, int C, int wide, u64 *__restrict__ coarse, const InitArgs ia)
 {
     // First kernel of the call: wait for everything earlier on the stream, THEN let the per-point kernel start -- its
     // CTAs read `points` before their own dependency wait, which is only safe once the producer of the points is done.
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x;
-    if (blockIdx.x > 0 || !wide) {
-        const int64_t nb = gridDim.x - (wide ? 1 : 0), b = blockIdx.x - (wide ? 1 : 0);
-        const int4 ff = make_int4(-1, -1, -1, -1), zz = make_int4(0, 0, 0, 0);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-            for (int64_t i = b * 1024 + tid; i < ia.ff_n[r]; i += nb * 1024) ia.ff_ptr[r][i] = ff;
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-            for (int64_t i = b * 1024 + tid; i < ia.z_n[r]; i += nb * 1024) ia.z_ptr[r][i] = zz;
-        return;
-    }
-    __shared__ u64 s[SAMPLE];
-    for (int i = tid; i < SAMPLE; i += 1024) {
-        // evenly spaced sample; short inputs are padded with +inf keys
-        int64_t idx = (n >= SAMPLE) ? (int64_t)i * (n / SAMPLE) : i;
-        u64 k = ~0ull;
-        if (idx < n) k = ((u64)refl_key_hi(points[idx * C + 3]) << 32) | (uint32_t)idx;
-        s[i] = k;
-    }
-    __syncthreads();
-    {
-        // bitonic sort, one key per thread (SAMPLE == blockDim): partners less than a warp apart exchange with
-        // shuffles (40 of the 55 steps), the others through shared memory
-        u64 k = s[tid];
-        for (int size = 2; size <= SAMPLE; size <<= 1) {
-            const bool up = (tid & size) == 0;
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                u64 o;
-                if (stride >= 32) {
-                    __syncthreads();
-                    s[tid] = k;
-                    __syncthreads();
-                    o = s[tid ^ stride];
-                } else {
-                    const unsigned lo = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)k, stride);
-                    const unsigned hi = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)(k >> 32), stride);
-                    o = ((u64)hi << 32) | lo;
-                }
-                const bool lower = (tid & stride) == 0;
-                const bool take_min = lower == up;
-                k = take_min ? (k < o ? k : o) : (k < o ? o : k);
-            }
+    __shared__ u64 s[CSAMPLE];
+    if (wide && blockIdx.x == 0) {
+        if (tid < CSAMPLE) s[tid] = sample_key(points, n, C, tid, CSAMPLE);
+        __syncthreads();
+        if (tid < CSAMPLE) {
+            const u64 k = s[tid];
+            int rank = 0;
+#pragma unroll 8
+            for (int j = 0; j < CSAMPLE; ++j) rank += (s[j] < k) ? 1 : 0;       // keys are unique (index in the low word)
+            if (rank >= 1 && (rank & (rank - 1)) == 0 && rank < CSAMPLE)        // 1 2 4 ... 64 -> splitter 0 ... 6
+                coarse[31 - __clz(rank)] = k;
         }
-        __syncthreads();
-        s[tid] = k;
-        __syncthreads();
     }
-    // chunk b >= 1 starts at the geometric quantile chunk_sample_index(b); splitter i is the start of chunk i + 1
-    if (tid < NCH - 1) coarse[tid] = s[chunk_sample_index(tid + 1)];
-    for (int i = tid; i < NFINE - 1; i += 1024) fine[i] = s[(i + 1) * (SAMPLE / NFINE)];
+    const int4 ff = make_int4(-1, -1, -1, -1), zz = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        for (int64_t i = (int64_t)blockIdx.x * 1024 + tid; i < ia.ff_n[r]; i += (int64_t)gridDim.x * 1024) ia.ff_ptr[r][i] = ff;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+        for (int64_t i = (int64_t)blockIdx.x * 1024 + tid; i < ia.z_n[r]; i += (int64_t)gridDim.x * 1024) ia.z_ptr[r][i] = zz;
 }
 
 // ---- slot of a cell ------------------------------------------------------------------------------------------
@@ -253,113 +252,151 @@ __device__ __forceinline__ uint32_t hash_cell(uint32_t cell, int bits) { return 
 
 // Open addressing, linear probing.  A slot's key goes from -1 to a cell once and never changes, so the CAS that
 // inserts a key is also its publication: nobody waits for anybody.
-template <bool INSERT>
-__device__ __forceinline__ int hash_slot(const VoxBuf &w, int32_t cell)
+__device__ __forceinline__ int hash_insert(const VoxBuf &w, int32_t cell)
 {
     const uint32_t mask = (1u << w.hash_bits) - 1u;
     uint32_t h = hash_cell((uint32_t)cell, w.hash_bits);
     for (uint32_t probe = 0; probe <= mask; ++probe) {
         int32_t k = __ldcg(w.slot_key + h);
-        if (k == cell) return (int)h;
-        if (k == -1) {
-            if (!INSERT) return -1;                       // cannot happen: every cell was inserted by kernel A
-            k = atomicCAS(w.slot_key + h, -1, cell);
-            if (k == -1 || k == cell) return (int)h;
-        }
+        if (k == -1) k = atomicCAS(w.slot_key + h, -1, cell);
+        if (k == -1 || k == cell) return (int)h;
         h = (h + 1) & mask;
     }
-    return -1;
+    return -1;                                            // (a table of 2 n slots cannot fill up)
+}
+
+// The fine splitters of the ranking bins, needed three kernels later, come from SPL_CTAS extra CTAs of the per-point count
+// kernel, off the critical path: each stages the key sample in shared memory and ranks its share of it by counting
+// (no sorting network, no barrier chain); the key of rank r is splitter r - 1.
+constexpr int SPL_CTAS = SAMPLE / VOX_THREADS;
+
+__device__ void fine_splitters(const float *__restrict__ points, int64_t n, int C, u64 *__restrict__ fine, int part)
+{
+    __shared__ u64 s[SAMPLE];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < SAMPLE; i += VOX_THREADS) s[i] = sample_key(points, n, C, i, SAMPLE);
+    __syncthreads();
+    const int me = part * VOX_THREADS + tid;
+    const u64 k = s[me];
+    int rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < SAMPLE; ++j) {
+        count_if_less(rank, s[j], k);                         // (the sample keys are distinct, pads included)
+    }
+    if (rank >= 1) fine[rank - 1] = k;
 }
 
 // ---- A: per point, count ---------------------------------------------------------------------------------------
-constexpr int CNT_IT = 4;      // points per thread: the four point loads are in flight together; the counter updates
-                               // return nothing, so nothing else in this kernel waits on memory
+constexpr int CNT_IT = 4;      // points per thread: the four point loads, then the four atomics, are in flight together
 
-template <typename K, bool HASH>
-__global__ void __launch_bounds__(VOX_THREADS)
-vox_count_kernel(const float *__restrict__ points, int64_t n, const VoxParams prm, const int32_t *__restrict__ perm,
-                 const VoxBuf w, const FillArgs fa)
+template <typename K, bool HASH, bool VEC4, bool PERM>
+__global__ void __launch_bounds__(VOX_THREADS, 7)      // 7 x 148 = 1036 CTAs resident: 1e6 points (977 CTAs) are one wave
+vox_count_kernel(const float *__restrict__ points, int n, const VoxParams prm, const int32_t *__restrict__ perm,
+                 int pt_blocks, const VoxBuf w, const FillArgs fa)
 {
     // PDL: the points are read and binned into cells BEFORE the dependency wait, i.e. while the init kernel (workspace
-    // fill, sample sort) is still running; nothing the init kernel writes is touched before it.
+    // fill, sample ranking) is still running; nothing the init kernel writes is touched before it.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     constexpr bool WIDE = sizeof(K) == 8;
+    // the extra CTAs (64-bit keys) come first in the grid so that they start with the first wave; they read only caller memory
+    const int nspl = (int)gridDim.x - pt_blocks, blk = (int)blockIdx.x - nspl;
+    if (blk < 0) {
+        fine_splitters(points, n, prm.C, w.fine, (int)blockIdx.x);
+        return;
+    }
     __shared__ u64 s_split[NCH];
-    const int64_t p0 = (int64_t)blockIdx.x * (VOX_THREADS * CNT_IT) + threadIdx.x;
+    const int p0 = blk * (VOX_THREADS * CNT_IT) + threadIdx.x;
     int32_t cell[CNT_IT];
     float refl[CNT_IT];
 #pragma unroll
     for (int k = 0; k < CNT_IT; ++k) {
-        const int64_t p = p0 + k * VOX_THREADS;
+        const int p = p0 + k * VOX_THREADS;
         cell[k] = -1;
         refl[k] = 0.f;
         if (p >= n) continue;
-        const int64_t idx = perm ? (int64_t)(uint32_t)perm[p] : p;
+        const uint32_t idx = PERM ? (uint32_t)perm[p] : (uint32_t)p;
         float x, y, z;
-        if (prm.vec4) {
+        if (VEC4) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(points) + idx);
             x = v.x; y = v.y; z = v.z; refl[k] = v.w;
         } else {
-            const float *pt = points + idx * prm.C;
+            const float *pt = points + (size_t)idx * prm.C;
             x = __ldg(pt); y = __ldg(pt + 1); z = __ldg(pt + 2);
             if (WIDE) refl[k] = __ldg(pt + 3);
         }
         cell[k] = point_cell(prm, x, y, z);
     }
-    fill_slice(fa, 0);
+    fill_slice(fa, 0, blk, pt_blocks);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    PP_T0(w.counters, 1);
     if (WIDE) {
-        if (threadIdx.x < NCH - 1) s_split[threadIdx.x] = w.coarse[threadIdx.x];
+        if (threadIdx.x < NCH) s_split[threadIdx.x] = threadIdx.x < NCH - 1 ? w.coarse[threadIdx.x] : ~0ull;
         __syncthreads();
+    }
+    uint32_t r[CNT_IT], hi[CNT_IT], tick[CNT_IT];
+#pragma unroll
+    for (int k = 0; k < CNT_IT; ++k) {
+        const int p = p0 + k * VOX_THREADS;
+        r[k] = 0xFFFFFFFFu; hi[k] = 0u; tick[k] = 0u;
+        if (cell[k] < 0) continue;
+        int chunk;
+        if (WIDE) {
+            hi[k] = refl_key_hi(refl[k]);
+            const u64 key = ((u64)hi[k] << 32) | (uint32_t)p;
+            chunk = 0;                                    // number of splitters <= key (entry 7 is +inf): three steps
+#pragma unroll
+            for (int step = NCH / 2; step > 0; step >>= 1) chunk += (s_split[chunk + step - 1] <= key) ? step : 0;
+        } else {
+            chunk = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
+        }
+        const int slot = HASH ? hash_insert(w, cell[k]) : cell[k];
+        if (slot < 0) continue;
+        tick[k] = atomicAdd(w.cnt + (size_t)slot * NCH + chunk, 1u);
+        r[k] = ((uint32_t)slot << 3) | (uint32_t)chunk;
     }
 #pragma unroll
     for (int k = 0; k < CNT_IT; ++k) {
-        const int64_t p = p0 + k * VOX_THREADS;
+        const int p = p0 + k * VOX_THREADS;
         if (p >= n) continue;
-        uint32_t r = 0xFFFFFFFFu, hi = 0u;
-        if (cell[k] >= 0) {
-            int chunk = 0;
-            if (WIDE) {
-                hi = refl_key_hi(refl[k]);
-                const u64 key = ((u64)hi << 32) | (uint32_t)p;
-#pragma unroll
-                for (int c = 0; c < NCH - 1; ++c) chunk += (s_split[c] <= key) ? 1 : 0;
-            } else {
-                chunk = geo_bin<C_OCT, C_SUB>((uint32_t)p, prm.bits);
-            }
-            const int slot = HASH ? hash_slot<true>(w, cell[k]) : cell[k];
-            if (slot >= 0) {                                  // (a hash table of 2 n slots cannot fill up)
-                atomicAdd(w.cnt + (size_t)slot * NCH + chunk, 1u);
-                r = ((uint32_t)slot << 3) | (uint32_t)chunk;
-            }
+        w.rec_slot[p] = r[k];
+        if (r[k] != 0xFFFFFFFFu) {
+            w.rec_tick[p] = tick[k];
+            if (WIDE) w.rec_hi[p] = hi[k];
         }
-        if (WIDE) w.rec2[p] = make_uint2(r, hi);
-        else w.rec[p] = r;
     }
+    PP_T1(w.counters, 2);
 }
 
 // ---- B: per slot -------------------------------------------------------------------------------------------------
 // counts -> saturation chunk (the first chunk at which the cell holds max_points points; later chunks are dropped
 // unseen) and m = the points of the chunks up to it.  Segment offsets and the compact ids q come from CTA-wide prefix
-// sums and one atomic per CTA and counter.
+// sums and one atomic per CTA and counter; the eight counters of the slot become the write positions of its chunks.
 constexpr int CELLS_THREADS = 1024;
 
 __global__ void __launch_bounds__(CELLS_THREADS) vox_cells_kernel(const VoxParams prm, const VoxBuf w)
 {
-    pdl_enter();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    PP_T0(w.counters, 4);
     __shared__ u64 s_warp[CELLS_THREADS / 32];
     __shared__ u64 s_cta;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t t = (int64_t)blockIdx.x * CELLS_THREADS + tid;
-    uint32_t total = 0, m = 0;
-    int sat = NCH - 1;
+    uint32_t c[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) c[k] = 0u;
     if (t < w.T) {
         const uint4 a = *reinterpret_cast<const uint4 *>(w.cnt + (size_t)t * NCH);
         const uint4 b = *reinterpret_cast<const uint4 *>(w.cnt + (size_t)t * NCH + 4);
-        const uint32_t c[NCH] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    }
+    uint32_t total = 0, m = 0, n0 = 0;
+    int sat = NCH - 1;
+    {
         bool found = false;
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
+            if (n0 == 0) n0 = c[k];                       // keys in the first occupied chunk: the smallest key is one of them
             total += c[k];
             if (!found && total >= (uint32_t)prm.P) { found = true; sat = k; m = total; }
         }
@@ -395,69 +432,92 @@ __global__ void __launch_bounds__(CELLS_THREADS) vox_cells_kernel(const VoxParam
         }
     }
     __syncthreads();
+    PP_T1(w.counters, 5);
     if (!occ) return;
     const u64 excl = s_warp[warp] + incl - mine;
     const uint32_t q = (uint32_t)s_cta + (uint32_t)(excl & 0x7FFull);
     const uint32_t off = (uint32_t)(s_cta >> 32) + (uint32_t)(excl >> 11);
-    *reinterpret_cast<uint2 *>(w.cnt + (size_t)t * NCH) = make_uint2(off, (uint32_t)sat);
+    uint32_t pos[NCH], run = off;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        pos[k] = k <= sat ? run : DROPPED;
+        run += c[k];
+    }
+    *reinterpret_cast<uint4 *>(w.cnt + (size_t)t * NCH) = make_uint4(pos[0], pos[1], pos[2], pos[3]);
+    *reinterpret_cast<uint4 *>(w.cnt + (size_t)t * NCH + 4) = make_uint4(pos[4], pos[5], pos[6], pos[7]);
     const int cell = w.hash_bits ? w.slot_key[t] : (int)t;
-    w.qinfo[q] = make_int4(cell, (int)off, (int)m, (int)total);
+    w.qinfo[q] = make_int4(cell, (int)off, (int)m, (int)n0);
+    const int cx = cell % prm.g[0], tt = cell / prm.g[0];
+    w.qxyz[q] = make_int4(cx, tt % prm.g[1], tt / prm.g[1], 0);
 }
 
 // ---- C: per point, place -------------------------------------------------------------------------------------------
 constexpr int PLACE_IT = 4;
 
 template <typename K>
-__global__ void __launch_bounds__(VOX_THREADS) vox_place_kernel(int64_t n, const VoxBuf w, const FillArgs fa)
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_place_kernel(int n, const VoxBuf w, const FillArgs fa)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    fill_slice(fa, 1);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     constexpr bool WIDE = sizeof(K) == 8;
-    const int64_t p0 = (int64_t)blockIdx.x * (VOX_THREADS * PLACE_IT) + threadIdx.x;
-    uint32_t r[PLACE_IT], hi[PLACE_IT];
+    fill_slice(fa, 1, blockIdx.x, gridDim.x);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    PP_T0(w.counters, 7);
+    const int p0 = blockIdx.x * (VOX_THREADS * PLACE_IT) + threadIdx.x;
+    // the three record streams are read up front (coalesced, independent); the only dependent access of a point is
+    // the write position of its (cell, chunk)
+    uint32_t r[PLACE_IT], tick[PLACE_IT], hi[PLACE_IT];
 #pragma unroll
     for (int k = 0; k < PLACE_IT; ++k) {
-        const int64_t p = p0 + k * VOX_THREADS;
-        r[k] = 0xFFFFFFFFu;
-        hi[k] = 0u;
+        const int p = p0 + k * VOX_THREADS;
+        r[k] = 0xFFFFFFFFu; tick[k] = 0u; hi[k] = 0u;
         if (p < n) {
-            if (WIDE) { const uint2 v = w.rec2[p]; r[k] = v.x; hi[k] = v.y; }
-            else r[k] = w.rec[p];
+            r[k] = __ldcs(w.rec_slot + p);
+            tick[k] = __ldcs(w.rec_tick + p);
+            if (WIDE) hi[k] = __ldcs(w.rec_hi + p);
         }
     }
-    uint32_t sat[PLACE_IT];
-#pragma unroll
-    for (int k = 0; k < PLACE_IT; ++k)
-        sat[k] = r[k] != 0xFFFFFFFFu ? __ldcg(w.cnt + (size_t)(r[k] >> 3) * NCH + 1) : 0u;
     uint32_t pos[PLACE_IT];
 #pragma unroll
-    for (int k = 0; k < PLACE_IT; ++k) {
-        pos[k] = 0xFFFFFFFFu;
-        if (r[k] != 0xFFFFFFFFu && (r[k] & 7u) <= sat[k]) pos[k] = atomicAdd(w.cnt + (size_t)(r[k] >> 3) * NCH, 1u);
-    }
+    for (int k = 0; k < PLACE_IT; ++k)          // (slot << 3 | chunk) is the index of the chunk's write position
+        pos[k] = r[k] != 0xFFFFFFFFu ? __ldg(w.cnt + r[k]) : DROPPED;
 #pragma unroll
     for (int k = 0; k < PLACE_IT; ++k) {
-        if (pos[k] == 0xFFFFFFFFu) continue;
-        const int64_t p = p0 + k * VOX_THREADS;
-        ((K *)w.seg)[pos[k]] = WIDE ? (K)(((u64)hi[k] << 32) | (uint32_t)p) : (K)(uint32_t)p;
+        if (pos[k] == DROPPED) continue;
+        const int p = p0 + k * VOX_THREADS;
+        ((K *)w.seg)[pos[k] + tick[k]] = WIDE ? (K)(((u64)hi[k] << 32) | (uint32_t)p) : (K)(uint32_t)p;
     }
+    PP_T1(w.counters, 8);
 }
 
-// ---- F: per cell, smallest key and its ranking bin ---------------------------------------------------------------
-// Bins (monotone in the key).  64-bit keys: sample interval of the key, then a linear position inside the interval on
-// the reflectance bits.  A cell with m points has its smallest key near the 1/m quantile, so the smallest keys crowd
-// into the first ~ nq / n of the key space: the intervals below `istar` share most of the bins.
+// ---- H: per cell, smallest key, ranking bin; the last CTA: bucket order and cutoff ---------------------------------
+// Ranking bins, monotone in the key.  A key is first located on a scale of NFINE quantile intervals: interval i and a
+// linear position frac in [0, 1) inside it (64-bit keys: the 1023 sample splitters + interpolation on the whole key, so
+// keys that tie on the reflectance spread by their index; 32-bit keys: the position itself).  A cell with m points has
+// its smallest key near the 1/m quantile and cell sizes span decades, so the bins are laid out logarithmically in
+// x = i + frac + x0 (x0 = the mean 1/m in intervals): interval i still owns at least one bin.  The logarithm is the
+// float's own bit pattern (monotone and exact in integer arithmetic: pillar ids must not depend on rounding).
 struct BinPlan {
-    int istar, nsub;
+    float x0;
+    int l0;
+    unsigned long long mul;
 };
 __device__ __forceinline__ BinPlan bin_plan(int nq, int64_t n_points)
 {
     BinPlan b;
-    int istar = (int)(((int64_t)NFINE * 3 * nq) / (n_points > 0 ? n_points : 1)) + 8;
-    b.istar = istar > NFINE - 1 ? NFINE - 1 : istar;
-    b.nsub = (NBIN - NFINE) / b.istar;
+    float x0 = (float)NFINE * (float)nq / (float)(n_points > 0 ? n_points : 1);
+    b.x0 = x0 < 0.5f ? 0.5f : x0;
+    b.l0 = __float_as_int(b.x0);
+    const unsigned long long span = (unsigned long long)(__float_as_int((float)NFINE + b.x0) - b.l0);
+    b.mul = ((unsigned long long)(NBIN - NFINE - 1) << 32) / span;
     return b;
+}
+__device__ __forceinline__ int log_bin(const BinPlan bp, int i, float frac)
+{
+    frac = frac < 0.f ? 0.f : (frac > 0.99999994f ? 0.99999994f : frac);
+    const float x = ((float)i + bp.x0) + frac;                          // monotone in (i, frac)
+    const unsigned long long l = (unsigned long long)(__float_as_int(x) - bp.l0);
+    return i + (int)((l * bp.mul) >> 32);
 }
 
 __device__ __forceinline__ int wide_bin(const u64 *s_fine, const BinPlan bp, u64 f)
@@ -468,125 +528,150 @@ __device__ __forceinline__ int wide_bin(const u64 *s_fine, const BinPlan bp, u64
         if (s_fine[mid] <= f) lo = mid + 1; else hi = mid;
     }
     const int i = lo;
-    if (i >= bp.istar) return bp.istar * bp.nsub + (i - bp.istar);
-    const uint32_t hi_w = (uint32_t)(s_fine[i] >> 32);
-    uint32_t lo_w;
-    if (i > 0) lo_w = (uint32_t)(s_fine[i - 1] >> 32);
-    else { const uint32_t a = (uint32_t)(s_fine[0] >> 32), b = (uint32_t)(s_fine[1] >> 32), wd = b - a; lo_w = a > wd ? a - wd : 0u; }
-    const uint32_t fw = (uint32_t)(f >> 32);
-    int sub = 0;
-    if (fw > lo_w) {
-        // monotone in f: conversion, multiplication by a positive constant and truncation are all monotone
-        const float inv = (float)bp.nsub / ((float)(hi_w - lo_w) + 1.0f);
-        sub = (int)((float)(fw - lo_w) * inv);
-    }
-    return i * bp.nsub + (sub < bp.nsub - 1 ? sub : bp.nsub - 1);
+    // interval i = [bot, top): bot = splitter i - 1 (or an extrapolation below the first), top = splitter i (or +inf)
+    u64 bot, top;
+    // (the outermost intervals are open: their far edge is extrapolated by twice the mean width of the 16 nearest
+    // intervals -- single intervals of a sample are far too irregular for that)
+    if (i > 0) bot = s_fine[i - 1];
+    else { const u64 wd = (s_fine[16] - s_fine[0]) / 8; bot = s_fine[0] > wd ? s_fine[0] - wd : 0ull; }
+    if (i < NFINE - 1) top = s_fine[i];
+    else { const u64 wd = (s_fine[NFINE - 2] - s_fine[NFINE - 18]) / 8; top = bot + wd > bot ? bot + wd : ~0ull; }
+    float frac = 0.f;
+    if (f > bot) frac = top > bot ? (float)(f - bot) / ((float)(top - bot) + 1.0f) : 0.f;      // monotone in f
+    return log_bin(bp, i, frac);
 }
 
-constexpr int FIRST_THREADS = 256, FIRST_GL = 8;      // 8 lanes per cell
+__device__ __forceinline__ int narrow_bin(const BinPlan bp, uint32_t p, int bits)
+{
+    // positions < 2^bits: the top 9 bits are the interval (NFINE = 2^9), the rest the fraction
+    if (bits <= 9) return log_bin(bp, (int)(p << (9 - bits)), 0.f);
+    const int sh = bits - 9;
+    return log_bin(bp, (int)(p >> sh), (float)(p & ((1u << sh) - 1u)) / (float)(1u << sh));
+}
+
+constexpr int RANK_THREADS = 1024;
 
 template <typename K>
-__global__ void __launch_bounds__(FIRST_THREADS)
-vox_first_kernel(const VoxParams prm, const VoxBuf w, int64_t n_points, const FillArgs fa)
+__global__ void __launch_bounds__(RANK_THREADS)
+vox_rank_kernel(const VoxParams prm, const VoxBuf w, int64_t n_points)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    fill_slice(fa, 2);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    PP_T0(w.counters, 10);
     constexpr bool WIDE = sizeof(K) == 8;
     __shared__ u64 s_fine[NFINE];
-    if (WIDE) {
-        for (int i = threadIdx.x; i < NFINE - 1; i += FIRST_THREADS) s_fine[i] = w.fine[i];
-        if (threadIdx.x == 0) s_fine[NFINE - 1] = ~0ull;
-        __syncthreads();
-    }
+    const int tid = threadIdx.x, lane = tid & 31;
     const int nq = w.counters[CTR_NQ];
-    const BinPlan bp = bin_plan(nq, n_points);
-    const int lane = threadIdx.x & 31, sub = lane & (FIRST_GL - 1);
     const K *seg = (const K *)w.seg;
-    const int groups = gridDim.x * (FIRST_THREADS / FIRST_GL);
-    for (int q0 = blockIdx.x * (FIRST_THREADS / FIRST_GL); q0 < nq; q0 += groups) {
-        const int q = q0 + threadIdx.x / FIRST_GL;
-        K mn = KeyInf<K>::value();
-        if (q < nq) {
-            const int4 info = w.qinfo[q];
-            for (int j = sub; j < info.z; j += FIRST_GL) {
-                const K k = seg[info.y + j];
-                mn = k < mn ? k : mn;
-            }
+    constexpr int GL = 8, CPB = RANK_THREADS / GL;    // 8 lanes per cell: the keys of the first chunk are read side by side
+    if ((int64_t)blockIdx.x * CPB < nq) {
+        if (WIDE) {
+            for (int i = tid; i < NFINE - 1; i += RANK_THREADS) s_fine[i] = w.fine[i];
+            if (tid == 0) s_fine[NFINE - 1] = ~0ull;
+            __syncthreads();
         }
+        const BinPlan bp = bin_plan(nq, n_points);
+        const int sub = lane & (GL - 1);
+        for (int q0 = blockIdx.x * CPB; q0 < nq; q0 += gridDim.x * CPB) {
+            const int q = q0 + tid / GL;
+            K mn = KeyInf<K>::value();
+            if (q < nq) {
+                const int4 info = w.qinfo[q];
+                for (int j = sub; j < info.w; j += GL) {      // the segment is ordered by chunk: the first chunk holds the minimum
+                    const K k = seg[info.y + j];
+                    mn = k < mn ? k : mn;
+                }
+            }
 #pragma unroll
-        for (int o = FIRST_GL / 2; o > 0; o >>= 1) {
-            K x;
-            if (WIDE) {
-                const unsigned lo = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)mn, o), hi = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)((u64)mn >> 32), o);
-                x = (K)(((u64)hi << 32) | lo);
-            } else {
-                x = (K)__shfl_xor_sync(0xFFFFFFFFu, (unsigned)mn, o);
+            for (int o = GL / 2; o > 0; o >>= 1) {
+                K x;
+                if (WIDE) {
+                    const unsigned lo = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)mn, o), hi = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)((u64)mn >> 32), o);
+                    x = (K)(((u64)hi << 32) | lo);
+                } else {
+                    x = (K)__shfl_xor_sync(0xFFFFFFFFu, (unsigned)mn, o);
+                }
+                mn = x < mn ? x : mn;
             }
-            mn = x < mn ? x : mn;
-        }
-        if (q < nq && sub == 0) {
-            const int bin = WIDE ? wide_bin(s_fine, bp, (u64)mn) : geo_bin<F_OCT, F_SUB>((uint32_t)mn, prm.bits);
-            ((K *)w.first)[q] = mn;
-            w.bin_of_q[q] = bin;
-            w.arr_of_q[q] = atomicAdd(w.hist + bin, 1);
+            if (q < nq && sub == 0) {
+                const int bin = WIDE ? wide_bin(s_fine, bp, (u64)mn) : narrow_bin(bp, (uint32_t)mn, prm.bits);
+                ((K *)w.first)[q] = mn;
+                w.bin_of_q[q] = bin;
+                w.arr_of_q[q] = atomicAdd(w.hist + bin, 1);
+            }
         }
     }
+    PP_T1(w.counters, 11);
 }
 
-// ---- R: cells in bucket order; cutoff ------------------------------------------------------------------------------
+// ---- R: cells in bucket order; cutoff -------------------------------------------------------------------------------
+// Every cell's first key goes to lkey[base[bin] + arrival index]: the cells of a bin are contiguous, so the gather
+// kernel ranks a cell against its bin with coalesced reads whatever the distribution of the keys.  The last CTA to
+// finish settles the cutoff.
 constexpr int BUCKET_THREADS = 1024;
 
 template <typename K>
 __global__ void __launch_bounds__(BUCKET_THREADS)
 vox_bucket_kernel(const VoxParams prm, const VoxBuf w, int32_t *__restrict__ voxel_num)
 {
-    pdl_enter();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    PP_T0(w.counters, 13);
     __shared__ int s_base[NBIN + 1];
     __shared__ int s_warp[BUCKET_THREADS / 32];
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nq = w.counters[CTR_NQ];
-    {
-        constexpr int PER = NBIN / BUCKET_THREADS;
-        int v[PER], sum = 0;
+    const bool work = (int64_t)blockIdx.x * BUCKET_THREADS < nq;
+    if (work || blockIdx.x == 0) {
+        // exclusive scan of the bin histogram, every CTA for itself (warp w scans bins [w, w + 1) * PERW, coalesced)
+        constexpr int PERW = NBIN / (BUCKET_THREADS / 32), ITS = PERW / 32;
+        int ex[ITS], carry = 0;
 #pragma unroll
-        for (int k = 0; k < PER; ++k) { v[k] = w.hist[tid * PER + k]; sum += v[k]; }
-        int incl = sum;
+        for (int it = 0; it < ITS; ++it) {
+            const int v = w.hist[warp * PERW + it * 32 + lane];
+            int incl = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            ex[it] = carry + incl - v;
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        if (lane == 31) s_warp[warp] = incl;
+        if (lane == 0) s_warp[warp] = carry;
         __syncthreads();
-        int base = incl - sum;
-        for (int k = 0; k < warp; ++k) base += s_warp[k];
+        int wbase = 0;
+        for (int k = 0; k < warp; ++k) wbase += s_warp[k];
 #pragma unroll
-        for (int k = 0; k < PER; ++k) { s_base[tid * PER + k] = base; base += v[k]; }
-        if (tid == BUCKET_THREADS - 1) s_base[NBIN] = base;
+        for (int it = 0; it < ITS; ++it) s_base[warp * PERW + it * 32 + lane] = wbase + ex[it];
+        if (tid == BUCKET_THREADS - 1) s_base[NBIN] = wbase + carry;
         __syncthreads();
+        if (blockIdx.x == 0) {
+            for (int i = tid; i <= NBIN; i += BUCKET_THREADS) w.base[i] = s_base[i];
+            if (tid == 0) *voxel_num = nq < prm.max_voxels ? nq : prm.max_voxels;
+        }
     }
-    if (blockIdx.x == 0) {
-        for (int i = tid; i <= NBIN; i += BUCKET_THREADS) w.base[i] = s_base[i];
-        if (tid == 0) *voxel_num = nq < prm.max_voxels ? nq : prm.max_voxels;
-    }
-    for (int q = blockIdx.x * BUCKET_THREADS + tid; q < nq; q += gridDim.x * BUCKET_THREADS) {
-        const int slot = s_base[w.bin_of_q[q]] + w.arr_of_q[q];
-        w.lq[slot] = q;
-        ((K *)w.lkey)[slot] = ((const K *)w.first)[q];
+    K *lkey = (K *)w.lkey;
+    for (int q = blockIdx.x * BUCKET_THREADS + tid; q < nq; q += gridDim.x * BUCKET_THREADS)
+        lkey[s_base[w.bin_of_q[q]] + w.arr_of_q[q]] = ((const K *)w.first)[q];
+    PP_T1(w.counters, 14);
+    if (nq <= prm.max_voxels) {
+        if (blockIdx.x == 0 && tid == 0) *(K *)w.cutoff = KeyInf<K>::value();
+        return;
     }
     // The reference breaks at the first point that would open pillar max_voxels + 1 (:223, :291): its key -- the cell
-    // minimum of rank max_voxels -- is the cutoff.  The last CTA to finish finds it in the bucket that holds that rank.
+    // minimum of rank max_voxels -- is the cutoff; it sits in the bin that holds that rank.  The last CTA to finish
+    // (one that scanned the histogram: CTA 0 always does) looks it up.
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(w.counters + CTR_DONE, 1) == (int)gridDim.x - 1) ? 1 : 0;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (nq <= prm.max_voxels) {
-        if (tid == 0) *(K *)w.cutoff = KeyInf<K>::value();
-        return;
+    if (!(work || blockIdx.x == 0)) {                 // (a CTA without cells did not scan: read CTA 0's copy)
+        for (int i = tid; i <= NBIN; i += BUCKET_THREADS) s_base[i] = __ldcg(w.base + i);
+        __syncthreads();
     }
     int lo = 0, hi = NBIN;                               // largest bin b with base[b] <= max_voxels
     while (lo < hi) {
@@ -594,14 +679,12 @@ vox_bucket_kernel(const VoxParams prm, const VoxBuf w, int32_t *__restrict__ vox
         if (s_base[mid] <= prm.max_voxels) lo = mid; else hi = mid - 1;
     }
     // base[NBIN] = nq > max_voxels, so lo < NBIN and base[lo + 1] > max_voxels: bin lo holds the rank max_voxels
-    const int b0 = s_base[lo], b1 = s_base[lo + 1];
-    const int target = prm.max_voxels - b0;
-    const K *lkey = (const K *)w.lkey;
+    const int b0 = s_base[lo], b1 = s_base[lo + 1], target = prm.max_voxels - b0;
     for (int i = b0 + tid; i < b1; i += BUCKET_THREADS) {
         const K f = __ldcg(lkey + i);
-        int cnt = 0;
-        for (int j = b0; j < b1; ++j) cnt += (__ldcg(lkey + j) < f) ? 1 : 0;
-        if (cnt == target) *(K *)w.cutoff = f;
+        int c = 0;
+        for (int j = b0; j < b1; ++j) c += (__ldcg(lkey + j) < f) ? 1 : 0;
+        if (c == target) *(K *)w.cutoff = f;
     }
 }
 
@@ -664,13 +747,54 @@ __device__ __forceinline__ void warp_merge_split(K &a, K &c, int lane)
     c = warp_bitonic_merge<K>(hi, lane);
 }
 
-// The R * 32 smallest keys of seg[0, m), ascending: element e = r * 32 + lane is b[r].  Batches of 32 keys are sorted
-// and merged down the registers; a batch with no key below the current last element is skipped after one ballot.
+constexpr int SEL_SMEM = 128;        // segments up to this many keys are ranked by counting in shared memory
+
+// Segment of at most NK * 32 keys: every key's rank = number of smaller keys of the segment (broadcast reads of the
+// staged segment: no shuffles, no sorting network), then the keys are put in rank order through shared memory.
+template <typename K, int R, int NK>
+__device__ __forceinline__ void rank_select(const K *__restrict__ seg, int m, int lane, K *s_keys, const K (&pre)[2], K (&b)[R])
+{
+    K k[NK];
+#pragma unroll
+    for (int t = 0; t < NK; ++t) {
+        k[t] = t < 2 ? pre[t] : ((t * 32 + lane < m) ? seg[t * 32 + lane] : KeyInf<K>::value());    // keys 0 .. 63 were prefetched
+        s_keys[t * 32 + lane] = k[t];
+    }
+    __syncwarp();
+    int rank[NK];
+#pragma unroll
+    for (int t = 0; t < NK; ++t) rank[t] = 0;
+#pragma unroll 4
+    for (int j = 0; j < m; ++j) {
+        const K o = s_keys[j];
+#pragma unroll
+        for (int t = 0; t < NK; ++t) count_if_less(rank[t], o, k[t]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NK; ++t)
+        if (t * 32 + lane < m && rank[t] < R * 32) s_keys[rank[t]] = k[t];      // ranks are a permutation: no collisions
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (r * 32 + lane < m) b[r] = s_keys[r * 32 + lane];
+    __syncwarp();
+}
+
+
+// The R * 32 smallest keys of seg[0, m), ascending: element e = r * 32 + lane is b[r].
+//   m <= SEL_SMEM  every key's rank = number of smaller keys of the segment (broadcast reads of the staged segment; no
+//                  shuffles, no sorting network); the keys are then put in rank order through shared memory
+//   longer         batches of 32 keys are sorted and merged down the registers; a batch with no key below the current
+//                  last element is skipped after one ballot
 template <typename K, int R>
-__device__ __forceinline__ void select_smallest(const K *__restrict__ seg, int m, int lane, K (&b)[R])
+__device__ __forceinline__ void select_smallest(const K *__restrict__ seg, int m, int lane, K *s_keys, const K (&pre)[2], K (&b)[R])
 {
 #pragma unroll
     for (int r = 0; r < R; ++r) b[r] = KeyInf<K>::value();
+    if (m <= 32) { rank_select<K, R, 1>(seg, m, lane, s_keys, pre, b); return; }
+    if (m <= 64) { rank_select<K, R, 2>(seg, m, lane, s_keys, pre, b); return; }
+    if (m <= SEL_SMEM) { rank_select<K, R, SEL_SMEM / 32>(seg, m, lane, s_keys, pre, b); return; }
     for (int i0 = 0; i0 < m; i0 += 32) {
         K c = (i0 + lane < m) ? seg[i0 + lane] : KeyInf<K>::value();
         if (i0 == 0) {
@@ -706,15 +830,15 @@ struct GatherOut {
 
 constexpr int GP_THREADS = 128;      // 4 pillars per CTA
 
-// pillar id of bucket slot s = bucket base + number of smaller keys inside the bucket (the whole warp counts)
+// pillar id of cell q = base of its bin + number of smaller first keys in the bin (the whole warp counts)
 template <typename K>
-__device__ __forceinline__ int pillar_rank(const VoxBuf &w, int s, int lane, int &q)
+__device__ __forceinline__ int pillar_rank(const VoxBuf &w, int q, int lane)
 {
-    const K *lkey = (const K *)w.lkey;
-    q = w.lq[s];
-    const K f = lkey[s];
+    const K f = ((const K *)w.first)[q];
     const int bin = w.bin_of_q[q];
     const int b0 = w.base[bin], b1 = w.base[bin + 1];
+    if (b1 - b0 == 1) return b0;                          // alone in its bin (the common case)
+    const K *lkey = (const K *)w.lkey;
     int cnt = 0;
     for (int j = b0 + lane; j < b1; j += 32) cnt += (lkey[j] < f) ? 1 : 0;
 #pragma unroll
@@ -722,12 +846,11 @@ __device__ __forceinline__ int pillar_rank(const VoxBuf &w, int s, int lane, int
     return b0 + cnt;
 }
 
-__device__ __forceinline__ void write_coors(const VoxParams &prm, const GatherOut &out, int pid, int cell)
+__device__ __forceinline__ void write_coors(const GatherOut &out, int pid, int cell, const int4 xyz)
 {
-    const int cx = cell % prm.g[0], tt = cell / prm.g[0];
-    out.coors[pid * 3 + 0] = cx;
-    out.coors[pid * 3 + 1] = tt % prm.g[1];
-    out.coors[pid * 3 + 2] = tt / prm.g[1];
+    out.coors[pid * 3 + 0] = xyz.x;
+    out.coors[pid * 3 + 1] = xyz.y;
+    out.coors[pid * 3 + 2] = xyz.z;
     if (out.pillar_map) out.pillar_map[cell] = pid;
 }
 
@@ -742,20 +865,27 @@ vox_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ 
     // the weights do not depend on the predecessor: load them before the dependency wait
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ __align__(16) float s_row[PFN ? (GP_THREADS / 32) * 32 * 4 : 4];
+    __shared__ __align__(16) K s_sel[(GP_THREADS / 32) * SEL_SMEM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PfnWeights pw;
     if (PFN) pfn_load_weights(pw, pa.W, pa.scale, pa.shift, pa.U, 4, lane);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    PP_T0(w.counters, 16);
     const int nq = w.counters[CTR_NQ];
     const K cutoff = *(const K *)w.cutoff;
     const int P = prm.P, C = prm.C;
-    for (int s = blockIdx.x * (GP_THREADS / 32) + warp; s < nq; s += gridDim.x * (GP_THREADS / 32)) {
-        int q;
-        const int pid = pillar_rank<K>(w, s, lane, q);
+    for (int q = blockIdx.x * (GP_THREADS / 32) + warp; q < nq; q += gridDim.x * (GP_THREADS / 32)) {
+        const int4 info = w.qinfo[q], xyz = w.qxyz[q];
+        // the first 64 keys of the segment are requested before the ranking loads: the two chains of dependent reads
+        // (cell -> keys, cell -> bin -> bucket) overlap
+        const K *seg = (const K *)w.seg + info.y;
+        K pre[2];
+        pre[0] = lane < info.z ? seg[lane] : KeyInf<K>::value();
+        pre[1] = lane + 32 < info.z ? seg[lane + 32] : KeyInf<K>::value();
+        const int pid = pillar_rank<K>(w, q, lane);
         if (pid >= prm.max_voxels) continue;
-        const int4 info = w.qinfo[q];
         K b[R];
-        select_smallest<K, R>((const K *)w.seg + info.y, info.z, lane, b);
+        select_smallest<K, R>(seg, info.z, lane, s_sel + warp * SEL_SMEM, pre, b);
         int n = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -765,7 +895,7 @@ vox_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ 
             if (!valid) b[r] = KeyInf<K>::value();
         }
         if (lane == 0) out.num_points[pid] = n;
-        if (lane == 1) write_coors(prm, out, pid, info.x);
+        if (lane == 1) write_coors(out, pid, info.x, xyz);
         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -790,11 +920,12 @@ vox_gather_kernel(const float *__restrict__ points, const int32_t *__restrict__ 
         if (PFN) {
             const int cell = info.x;
             // channel c of cell (z, y, x) sits at canvas[(c * D + z) * H * W + y * W + x] = canvas[c * plane + cell]
-            pfn_pillar4(pw, v0, P, n, cell % prm.g[0], (cell / prm.g[0]) % prm.g[1], pa.vx, pa.vy, pa.x_off, pa.y_off,
+            pfn_pillar4(pw, v0, P, n, xyz.x, xyz.y, pa.vx, pa.vy, pa.x_off, pa.y_off,
                         s_row + warp * 32 * 4, pa.feat ? pa.feat + (int64_t)pid * (pa.U + 1) : nullptr,
                         pa.canvas ? pa.canvas + cell : nullptr, pa.plane, pa.U, lane);
         }
     }
+    PP_T1(w.counters, 17);
 }
 
 // Any max_points: the rank of every key of the segment by counting (quadratic in the segment, which the chunk filter
@@ -809,11 +940,10 @@ vox_gather_any_kernel(const float *__restrict__ points, const int32_t *__restric
     const int nq = w.counters[CTR_NQ];
     const K cutoff = *(const K *)w.cutoff;
     const int P = prm.P, C = prm.C;
-    for (int s = blockIdx.x * (GP_THREADS / 32) + warp; s < nq; s += gridDim.x * (GP_THREADS / 32)) {
-        int q;
-        const int pid = pillar_rank<K>(w, s, lane, q);
+    for (int q = blockIdx.x * (GP_THREADS / 32) + warp; q < nq; q += gridDim.x * (GP_THREADS / 32)) {
+        const int4 info = w.qinfo[q], xyz = w.qxyz[q];
+        const int pid = pillar_rank<K>(w, q, lane);
         if (pid >= prm.max_voxels) continue;
-        const int4 info = w.qinfo[q];
         const K *seg = (const K *)w.seg + info.y;
         const int m = info.z;
         int kept = 0;
@@ -833,7 +963,7 @@ vox_gather_any_kernel(const float *__restrict__ points, const int32_t *__restric
         // ranks [0, kept) were written (the kept keys are the smallest); the padding is zero
         for (int i = kept * C + lane; i < P * C; i += 32) out.voxels[(int64_t)pid * P * C + i] = 0.f;
         if (lane == 0) out.num_points[pid] = kept;
-        if (lane == 1) write_coors(prm, out, pid, info.x);
+        if (lane == 1) write_coors(out, pid, info.x, xyz);
     }
 }
 
@@ -879,15 +1009,16 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
     r.b.cnt = a.take<uint32_t>((size_t)r.b.T * NCH);
     const size_t z1_bytes = (size_t)r.b.T * NCH * sizeof(uint32_t);
     r.b.base = a.take<int32_t>(NBIN + 1);
-    r.b.rec = wide ? nullptr : a.take<uint32_t>((size_t)n1);
-    r.b.rec2 = wide ? a.take<uint2>((size_t)n1) : nullptr;
+    r.b.rec_slot = a.take<uint32_t>((size_t)n1);
+    r.b.rec_tick = a.take<uint32_t>((size_t)n1);
+    r.b.rec_hi = wide ? a.take<uint32_t>((size_t)n1) : nullptr;
     r.b.seg = a.take<char>((size_t)n1 * ksz);
     r.b.qinfo = a.take<int4>((size_t)r.Q);
+    r.b.qxyz = a.take<int4>((size_t)r.Q);
     r.b.first = a.take<char>((size_t)r.Q * ksz);
     r.b.bin_of_q = a.take<int32_t>((size_t)r.Q);
     r.b.arr_of_q = a.take<int32_t>((size_t)r.Q);
     r.b.lkey = a.take<char>((size_t)r.Q * ksz);
-    r.b.lq = a.take<int32_t>((size_t)r.Q);
     r.b.coarse = a.take<u64>(NCH);
     r.b.fine = a.take<u64>(NFINE);
     *total = align_up(a.off);
@@ -900,39 +1031,51 @@ Carve carve(void *ws, int64_t n, const pp_voxel_cfg *c, bool wide, size_t *total
     return r;
 }
 
+template <typename K, bool HASH>
+void launch_count(int pt_blocks, cudaStream_t st, const float *points, int n, const VoxParams &prm, const int32_t *perm,
+                  const VoxBuf &w, const FillArgs &fa)
+{
+    const dim3 blk(VOX_THREADS), grid(pt_blocks + (sizeof(K) == 8 ? SPL_CTAS : 0));
+    if (prm.vec4) {
+        if (perm) launch_pdl(vox_count_kernel<K, HASH, true, true>, grid, blk, 0, st, points, n, prm, perm, pt_blocks, w, fa);
+        else launch_pdl(vox_count_kernel<K, HASH, true, false>, grid, blk, 0, st, points, n, prm, perm, pt_blocks, w, fa);
+    } else {
+        if (perm) launch_pdl(vox_count_kernel<K, HASH, false, true>, grid, blk, 0, st, points, n, prm, perm, pt_blocks, w, fa);
+        else launch_pdl(vox_count_kernel<K, HASH, false, false>, grid, blk, 0, st, points, n, prm, perm, pt_blocks, w, fa);
+    }
+}
+
 template <typename K>
 int run(const float *points, int64_t n, const VoxParams &prm, const int32_t *perm, const Carve &cv, float *voxels,
-        int32_t *coors, int32_t *num_points, int32_t *voxel_num, int32_t *pillar_map, int64_t max_rows, const PfnArgs *pfn,
-        cudaStream_t st)
+        int32_t *coors, int32_t *num_points, int32_t *voxel_num, int32_t *pillar_map, const PfnArgs *pfn, cudaStream_t st)
 {
     const VoxBuf &w = cv.b;
+    constexpr bool WIDE = sizeof(K) == 8;
     FillArgs fa = {nullptr, 0};
     if (pfn && pfn->canvas) {
         fa.base = pfn->canvas;
         fa.units = (int64_t)(pfn->U + 1) * pfn->plane / 8;
     }
-    constexpr bool WIDE = sizeof(K) == 8;
     int64_t fill_units = 0;
     for (int r = 0; r < 3; ++r) fill_units += cv.ia.ff_n[r];
     for (int r = 0; r < 2; ++r) fill_units += cv.ia.z_n[r];
     int init_blocks = (int)ceil_div(fill_units, 1024 * 4);
     init_blocks = init_blocks < 1 ? 1 : (init_blocks > 148 * 2 ? 148 * 2 : init_blocks);
-    launch_pdl(vox_init_kernel, dim3(init_blocks + (WIDE ? 1 : 0)), dim3(1024), 0, st, points, n, prm.C, WIDE ? 1 : 0, w.coarse, w.fine, cv.ia);
+    launch_pdl(vox_init_kernel, dim3(init_blocks), dim3(1024), 0, st, points, n, prm.C, WIDE ? 1 : 0, w.coarse, cv.ia);
     if (int rc = check_launch("vox_init_kernel")) return rc;
-    const unsigned pt_blocks = (unsigned)ceil_div(n, VOX_THREADS * CNT_IT);
-    if (w.hash_bits)
-        launch_pdl(vox_count_kernel<K, true>, dim3(pt_blocks), dim3(VOX_THREADS), 0, st, points, n, prm, perm, w, fa);
-    else
-        launch_pdl(vox_count_kernel<K, false>, dim3(pt_blocks), dim3(VOX_THREADS), 0, st, points, n, prm, perm, w, fa);
+    const int pt_blocks = (int)ceil_div(n, VOX_THREADS * CNT_IT);
+    if (w.hash_bits) launch_count<K, true>(pt_blocks, st, points, (int)n, prm, perm, w, fa);
+    else launch_count<K, false>(pt_blocks, st, points, (int)n, prm, perm, w, fa);
     if (int rc = check_launch("vox_count_kernel")) return rc;
     launch_pdl(vox_cells_kernel, dim3((unsigned)ceil_div(w.T, CELLS_THREADS)), dim3(CELLS_THREADS), 0, st, prm, w);
     if (int rc = check_launch("vox_cells_kernel")) return rc;
-    launch_pdl(vox_place_kernel<K>, dim3((unsigned)ceil_div(n, VOX_THREADS * PLACE_IT)), dim3(VOX_THREADS), 0, st, n, w, fa);
+    const int pl_blocks = (int)ceil_div(n, VOX_THREADS * PLACE_IT);
+    launch_pdl(vox_place_kernel<K>, dim3(pl_blocks), dim3(VOX_THREADS), 0, st, (int)n, w, fa);
     if (int rc = check_launch("vox_place_kernel")) return rc;
     // the cell count is only known on the device: grid-stride grids sized for the worst case, capped at a few waves
     auto capped = [](int64_t blocks, int64_t cap) { return (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap); };
-    launch_pdl(vox_first_kernel<K>, dim3(capped(ceil_div(cv.Q, FIRST_THREADS / FIRST_GL), 148 * 8)), dim3(FIRST_THREADS), 0, st, prm, w, n, fa);
-    if (int rc = check_launch("vox_first_kernel")) return rc;
+    launch_pdl(vox_rank_kernel<K>, dim3(capped(ceil_div(cv.Q, RANK_THREADS / 8), 148 * 2)), dim3(RANK_THREADS), 0, st, prm, w, n);
+    if (int rc = check_launch("vox_rank_kernel")) return rc;
     launch_pdl(vox_bucket_kernel<K>, dim3(capped(ceil_div(cv.Q, BUCKET_THREADS), 148)), dim3(BUCKET_THREADS), 0, st, prm, w, voxel_num);
     if (int rc = check_launch("vox_bucket_kernel")) return rc;
     GatherOut out = {voxels, coors, num_points, pillar_map};
@@ -1075,7 +1218,6 @@ static int voxelize_impl(const float *points, int64_t n, const pp_voxel_cfg *cfg
         }
     }
     const int32_t *order_perm = order == PP_ORDER_PERM ? perm : nullptr;
-    const int64_t max_rows = max_rows_of(n, cfg);
     PfnArgs pa, *pap = nullptr;
     if (pfn) {
         pa.W = pfn->weight; pa.scale = pfn->scale; pa.shift = pfn->shift; pa.feat = pfn->feat; pa.U = pfn->units;
@@ -1084,6 +1226,6 @@ static int voxelize_impl(const float *points, int64_t n, const pp_voxel_cfg *cfg
         pap = &pa;
     }
     if (wide)
-        return run<u64>(points, n, q, order_perm, cv, voxels, coors, num_points, voxel_num, pillar_map, max_rows, pap, st);
-    return run<uint32_t>(points, n, q, order_perm, cv, voxels, coors, num_points, voxel_num, pillar_map, max_rows, pap, st);
+        return run<u64>(points, n, q, order_perm, cv, voxels, coors, num_points, voxel_num, pillar_map, pap, st);
+    return run<uint32_t>(points, n, q, order_perm, cv, voxels, coors, num_points, voxel_num, pillar_map, pap, st);
 }
