@@ -270,6 +270,16 @@ PP_API int pp_head_select_decode(const float *cls, const float *reg, const float
 PP_API int pp_head_direction_fixup(float *boxes, const int32_t *dir_bits, int64_t K, float dir_offset, pp_stream_t stream);
 
 /*
+ * `_, topk_inds = max_scores.topk(nms_pre)` of Anchor3DHead.get_bboxes_single, model/PointPillars.py:1056-1065:
+ * rows (k) int64 = the indices of the k largest of scores (n), in descending score order; equal scores: lower index
+ * first (torch.topk leaves that order unspecified).  Radix select + ordered compaction + stable sort of the survivors;
+ * k is clamped to n.  Workspace: pp_head_topk_workspace_bytes(n, k).
+ */
+PP_API size_t pp_head_topk_workspace_bytes(int64_t n, int64_t k);
+PP_API int pp_head_topk(const float *scores, int64_t n, int64_t k, int64_t *rows, void *workspace, size_t workspace_bytes,
+                 pp_stream_t stream);
+
+/*
  * Target assignment reductions of Anchor3DHead.assign_bboxes, model/PointPillars.py:964-978, without the (G, A)
  * IoU matrix: for every anchor the best IoU over the ground truths and the FIRST ground truth reaching it (:968),
  * for every ground truth its best IoU over the anchors (:971), and the low-quality-match flag (:976-978):

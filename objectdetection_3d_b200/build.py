@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpp_b200.so")
-SOURCES = ["pp_api.cu", "pp_sort.cu", "pp_voxelize.cu", "pp_pillar.cu", "pp_boxes.cu", "pp_nms.cu", "pp_points.cu"]
+SOURCES = ["pp_api.cu", "pp_sort.cu", "pp_voxelize.cu", "pp_pillar.cu", "pp_boxes.cu", "pp_nms.cu", "pp_points.cu", "pp_topk.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -277,8 +277,10 @@ __device__ __forceinline__ int b3_clip(float (*p)[3], int n, const float g[3], f
         int m = 0;
         for (int i = 0; i < n; ++i) {
             const int j = (i + 1 == n) ? 0 : i + 1;
-            if (s[i] >= 0.f) { q[m][0] = p[i][0]; q[m][1] = p[i][1]; q[m][2] = p[i][2]; ++m; }
-            if ((s[i] > 0.f && s[j] < 0.f) || (s[i] < 0.f && s[j] > 0.f)) {
+            // (a convex polygon clipped by a slab gains at most two vertices; the bound check is for inputs whose signs
+            // alternate through rounding on near-degenerate, co-planar faces)
+            if (s[i] >= 0.f && m < B3_MAXV) { q[m][0] = p[i][0]; q[m][1] = p[i][1]; q[m][2] = p[i][2]; ++m; }
+            if (((s[i] > 0.f && s[j] < 0.f) || (s[i] < 0.f && s[j] > 0.f)) && m < B3_MAXV) {
                 const float t = s[i] / (s[i] - s[j]);
                 q[m][0] = p[i][0] + t * (p[j][0] - p[i][0]);
                 q[m][1] = p[i][1] + t * (p[j][1] - p[i][1]);
@@ -286,7 +288,7 @@ __device__ __forceinline__ int b3_clip(float (*p)[3], int n, const float g[3], f
                 ++m;
             }
         }
-        n = m < B3_MAXV ? m : B3_MAXV;
+        n = m;
         for (int i = 0; i < n; ++i) { p[i][0] = q[i][0]; p[i][1] = q[i][1]; p[i][2] = q[i][2]; }
     }
     return n;

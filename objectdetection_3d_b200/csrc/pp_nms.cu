@@ -636,11 +636,8 @@ extern "C" int pp_nms_mode(const float *boxes9, const float *scores, int64_t sco
     }
     PP_CUDA_TRY(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));     // scalars, look-back state, diagonal bands
     prof_mark("memset");
-    static bool attr_set = false;
-    if (!attr_set) {
-        PP_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
+    // per device and context, cheap: set on every call (a process may drive several GPUs, from several threads)
+    PP_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     const unsigned nb = (unsigned)ceil_div(N, NMS_THREADS);
     nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.sc + SC_N,
                                                    iou_mode, w.aux);

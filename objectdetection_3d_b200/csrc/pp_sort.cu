@@ -298,11 +298,8 @@ int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *k
         return PP_ERR_WORKSPACE;
     }
     if (n <= SMALL_MAX) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            PP_CUDA_TRY(cudaFuncSetAttribute(sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
-            attr_set = true;
-        }
+        // per device and context, cheap: set on every call (a process may drive several GPUs, from several threads)
+        PP_CUDA_TRY(cudaFuncSetAttribute(sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM));
         sort_small_kernel<<<1, SMALL_THREADS, SMALL_SMEM, st>>>(keys_in, vals_in, keys_out, vals_out, (int)n);
         return check_launch("sort_small_kernel");
     }

@@ -80,14 +80,40 @@ def voxelize_device(points, cfg, order, perm=None, want_map=False):
     return voxels, coors, num, voxel_num, pmap
 
 
-def points_to_voxel(points, voxel_size, coors_range, max_points, max_voxels, reflectance_sampling, perm=None):
+_numba_order = None
+
+
+def numba_reflectance_order(reflectance):
+    """The reference's own pre-order, ``points[:, 3].argsort()[::-1]`` under numba.njit (ops/ops_numba.py:262), computed
+    with numba itself on the host: among EQUAL reflectances numba's quicksort order is what the reference follows, and
+    it is not reproducible in parallel.  Only for ``exact_ties=True``; needs numba (the reference's own dependency)."""
+    global _numba_order
+    if _numba_order is None:
+        import numba
+
+        @numba.njit(cache=False)
+        def order(a):
+            return a.argsort()[::-1]
+        _numba_order = order
+    refl = np.ascontiguousarray(reflectance.detach().cpu().numpy() if isinstance(reflectance, torch.Tensor) else reflectance)
+    return np.ascontiguousarray(_numba_order(refl)).astype(np.int32)
+
+
+def points_to_voxel(points, voxel_size, coors_range, max_points, max_voxels, reflectance_sampling, perm=None,
+                    exact_ties=False):
     """ops/ops_numba.py:109-168.  Returns (voxels f32 [M,P,C], coors int32 [M,3] xyz, num int32 [M]).
 
-    reflectance_sampling=True: points[:, 3] descending (ties: lower index first; the reference's numba
-    quicksort order on ties can be replayed through ``perm``).  False: the reference shuffles the
-    caller's array in place (:190) and then takes the given order; so does this function.
+    reflectance_sampling=True: points[:, 3] descending.  Among EQUAL reflectances (real LiDAR intensity is quantised,
+    so ties are the rule) the GPU order is: lower index first, -0.0 == +0.0 -- deterministic, but not the order the
+    reference's numba quicksort happens to produce, so with ties the kept subset of an over-full pillar, the slot order
+    and the pillar ids can differ from the reference's.  ``exact_ties=True`` computes the reference's order with numba
+    on the host (one CPU argsort per call) and replays it: bit-exact with the reference on any input.  Any order can
+    be replayed through ``perm``.  reflectance_sampling=False: the reference shuffles the caller's array in place
+    (:190) and then takes the given order; so does this function.
     """
     is_numpy = isinstance(points, np.ndarray)
+    if exact_ties and reflectance_sampling and perm is None:
+        perm = numba_reflectance_order(points[:, 3])
     if is_numpy:
         if not reflectance_sampling and perm is None:
             np.random.shuffle(points)                                   # same side effect as :190
@@ -127,9 +153,9 @@ class VoxelGenerator:
         self._max_voxel_points = max_voxel_points
         self._max_voxels = max_voxels
 
-    def generate(self, points, max_voxels, cloud_range, reflectance_sampling):
+    def generate(self, points, max_voxels, cloud_range, reflectance_sampling, exact_ties=False):
         return points_to_voxel(points, self._voxel_size, cloud_range, self._max_voxel_points, max_voxels,
-                               reflectance_sampling)
+                               reflectance_sampling, exact_ties=exact_ties)
 
     @property
     def voxel_size(self):

@@ -24,13 +24,14 @@ class PointPillarsVoxelization(nn.Module):
     num_points int64 [M]) on ``device``.  points: numpy (N,C) float32 (the reference's contract) or a
     CUDA tensor."""
 
-    def __init__(self, device, voxel_size, point_cloud_range, max_voxel_points, max_voxels):
+    def __init__(self, device, voxel_size, point_cloud_range, max_voxel_points, max_voxels, exact_ties=False):
         super().__init__()
         self.point_cloud_range = np.array(point_cloud_range)
         self.voxel_size = np.array(voxel_size)
         self.max_voxel_points = max_voxel_points
         self.max_voxels = max_voxels
         self.device = device
+        self.exact_ties = exact_ties          # reproduce numba's order among equal reflectances (host argsort per call)
 
     def forward_device(self, points):
         """Device-resident variant: (voxels, coors xyz int32, num int32, voxel_num scalar) without the
@@ -43,7 +44,8 @@ class PointPillarsVoxelization(nn.Module):
         vg = VoxelGenerator(self.voxel_size, self.point_cloud_range, self.max_voxel_points, self.max_voxels)
         if isinstance(points, np.ndarray):
             points = torch.from_numpy(np.ascontiguousarray(points, dtype=np.float32)).to(self.device)
-        voxels, coords, num_points = vg.generate(points, self.max_voxels, self.point_cloud_range, True)
+        voxels, coords, num_points = vg.generate(points, self.max_voxels, self.point_cloud_range, True,
+                                                 exact_ties=self.exact_ties)
         out_coords = coords[:, [2, 1, 0]].to(torch.int64)
         return voxels, out_coords, num_points.to(torch.int64)
 
@@ -70,8 +72,15 @@ class PFNLayer(nn.Module):
         shift = n.bias - n.running_mean * scale
         return self.linear.weight.contiguous().float(), scale.contiguous().float(), shift.contiguous().float()
 
+    def _wants_grad(self, *tensors):
+        """The CUDA kernels are forward-only: with autograd recording and something to differentiate (frozen-BatchNorm
+        fine-tuning, saliency, a validation pass that backpropagates) the torch ops run instead, like the reference's."""
+        return torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                            any(t is not None and t.requires_grad for t in tensors))
+
     def forward(self, inputs, num_voxel_points=None, aligned_distance=None):
-        if self.training or self.mode != 'max' or aligned_distance is not None or not inputs.is_cuda:
+        if (self.training or self.mode != 'max' or aligned_distance is not None or not inputs.is_cuda
+                or self._wants_grad(inputs)):
             return self._forward_autograd(inputs, num_voxel_points, aligned_distance)
         M, P, Cin = inputs.shape
         w, scale, shift = self.folded()
@@ -147,12 +156,30 @@ class PillarFeatureNet(nn.Module):
                                            float(self.x_offset), float(self.y_offset), _ptr(out), _stream()))
         return out
 
+    def _decorate_autograd(self, features, num_points, coors):
+        """:490-521 as torch ops (only when the points themselves need gradients)."""
+        P = features.shape[1]
+        mean = features[:, :, :3].sum(dim=1, keepdim=True) / num_points.type_as(features).view(-1, 1, 1)
+        f_cluster = features[:, :, :3] - mean
+        cx = coors[:, 3].to(features.dtype).unsqueeze(1) * self.vx + self.x_offset
+        cy = coors[:, 2].to(features.dtype).unsqueeze(1) * self.vy + self.y_offset
+        f_center = torch.stack([features[:, :, 0] - cx, features[:, :, 1] - cy], dim=-1)
+        x = torch.cat([features, f_cluster, f_center], dim=-1)
+        mask = (num_points.view(-1, 1) > torch.arange(P, device=features.device).view(1, -1)).unsqueeze(-1)
+        return x * mask.type_as(x)
+
     def forward(self, features, num_points, coors):
         if not features.is_cuda:
             raise _lib.PPError("PillarFeatureNet: CUDA tensors required (no CPU fallback)")
         M, P, C = features.shape
         single = len(self.pfn_layers) == 1
-        if single and not self.training:
+        wants_grad = torch.is_grad_enabled() and (features.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if features.requires_grad and torch.is_grad_enabled():
+            x = self._decorate_autograd(features, num_points, coors)       # gradients w.r.t. the points: torch ops
+            for pfn in self.pfn_layers:
+                x = pfn(x, num_points)
+            return torch.cat((x.squeeze(1), num_points.view(-1, 1).to(x.dtype)), dim=-1)
+        if single and not self.training and not wants_grad:
             layer = self.pfn_layers[0]
             w, scale, shift = layer.folded()
             x = features.contiguous().float()
@@ -167,6 +194,20 @@ class PillarFeatureNet(nn.Module):
         for pfn in self.pfn_layers:
             x = pfn(x, num_points)
         return torch.cat((x.squeeze(1), num_points.view(-1, 1).to(x.dtype)), dim=-1)
+
+
+def head_topk(scores, k):
+    """Indices of the k largest of a 1-D CUDA float tensor, descending score, equal scores by lower index
+    (`scores.topk(k)[1]` of model/PointPillars.py:1058-1059 with a deterministic tie rule), on pp_head_topk."""
+    lib = _lib.load()
+    scores = scores.contiguous().float()
+    n = scores.numel()
+    k = min(int(k), n)
+    rows = torch.empty((k,), dtype=torch.int64, device=scores.device)
+    ws_bytes = int(lib.pp_head_topk_workspace_bytes(n, k))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=scores.device)
+    _lib.check(lib.pp_head_topk(_ptr(scores), n, k, _ptr(rows), _ptr(ws), ws_bytes, _stream()))
+    return rows
 
 
 class _DenseScatter(torch.autograd.Function):
@@ -291,8 +332,8 @@ class Anchor3DHead(nn.Module):
         if total > self.nms_pre:
             max_scores = torch.empty((total,), dtype=torch.float32, device=dev)
             _lib.check(lib.pp_head_max_scores(_ptr(cls), A, ncls, H, W, _ptr(max_scores), _stream()))
-            _, rows = max_scores.topk(self.nms_pre)                      # :1058-1059
-            rows, K = rows.contiguous(), self.nms_pre
+            rows = head_topk(max_scores, self.nms_pre)                   # :1058-1059
+            K = self.nms_pre
         gen = self.anchor_generator
         assert len(gen.ranges) == 1, "one anchor range (as in config.yaml:64)"
         fp = ctypes.POINTER(ctypes.c_float)

@@ -77,6 +77,17 @@ def test_voxelize_ties_documented_rule(pp, oracle):
     assert np.array_equal(c, oc) and np.array_equal(n, on) and np.array_equal(v, ov)
 
 
+def test_voxelize_exact_ties_option(pp):
+    """exact_ties=True: the reference's tie order (numba's own argsort on the host) replayed -> bit-exact with the
+    REFERENCE's output on quantised reflectance, without the oracle."""
+    pytest.importorskip("numba")
+    g = golden("vox_model_ties")
+    vs, rg, P, cap, _ = vox_args(g)
+    v, c, n = pp.ops_numba.points_to_voxel(g["points"].copy(), vs, rg, P, cap, True, exact_ties=True)
+    assert np.array_equal(c, g["coors"]) and np.array_equal(n, g["num"])
+    assert np.array_equal(v.view(np.uint32), g["voxels"].view(np.uint32))
+
+
 @pytest.mark.parametrize("kind,n,cap,P", [("dense", 1_000_000, 12000, 32), ("uniform", 1_000_000, 12000, 32),
                                            ("dense", 300_000, 3000, 32), ("forest", 120_000, 7500000, 50)])
 def test_voxelize_full_size_vs_oracle(pp, oracle, kind, n, cap, P):
@@ -230,6 +241,33 @@ def test_pfn_golden_and_oracle(pp, oracle, name):
     assert np.array_equal(canvas, g["canvas"])
     canvas = sc(cu(g["out"]), coors.int(), 1).cpu().numpy()
     assert np.array_equal(canvas, g["canvas"])
+
+
+def test_pfn_eval_mode_keeps_gradients(pp):
+    """eval() with autograd recording (frozen-BatchNorm fine-tuning, saliency): the forward-only kernels must not be
+    taken -- the output has a grad_fn, matches the kernel path and the weights / points receive gradients."""
+    g = golden("pfn_single64")
+    vs, rg = g["voxel_size"].tolist(), g["point_cloud_range"].tolist()
+    net = pp.pointpillars.PillarFeatureNet(4, [64], vs, rg).cuda().eval()
+    l = net.pfn_layers[0]
+    with torch.no_grad():
+        l.linear.weight.copy_(cu(g["w0"])); l.norm.weight.copy_(cu(g["gamma0"])); l.norm.bias.copy_(cu(g["beta0"]))
+        l.norm.running_mean.copy_(cu(g["mean0"])); l.norm.running_var.copy_(cu(g["var0"]))
+    voxels, num, coors = cu(g["voxels"]), cu(g["num"]), cu(g["coors"])
+    with torch.no_grad():
+        ref = net(voxels, num, coors)
+    out = net(voxels, num, coors)
+    assert out.grad_fn is not None
+    scale = float(np.abs(g["voxels"]).max())
+    assert_close_t1(out.detach().cpu().numpy(), ref.cpu().numpy(), atol=1e-6 * scale, what="autograd vs kernel path")
+    out.sum().backward()
+    assert l.linear.weight.grad is not None and float(l.linear.weight.grad.abs().sum()) > 0
+    v2 = voxels.clone().requires_grad_(True)
+    net(v2, num, coors).sum().backward()
+    assert v2.grad is not None and float(v2.grad.abs().sum()) > 0
+    for p_ in net.parameters():
+        p_.requires_grad_(False)
+    assert net(voxels, num, coors).grad_fn is None            # nothing to differentiate: the kernel path again
 
 
 def test_scatter_3d_batched_and_backward(pp, oracle):
@@ -430,6 +468,48 @@ def test_head_box3d_assign_runs(pp):
     assert torch.isfinite(ab).all()
 
 
+def test_extract_feats_sequence_batch3(pp, oracle):
+    """PointPillars.extract_feats up to the pseudo-image (model/PointPillars.py:94-134) restated on the mirrors:
+    three numpy frames -> voxel_layer each -> concat, batch index padded in front of the coordinates ->
+    voxel_encoder -> batch_size = coors[-1, 0] + 1 -> pseudoimage_generator, against the oracle frame by frame."""
+    import torch.nn.functional as F
+    from objectdetection_3d_b200 import synth
+    g, pfn = synth.G_KITTI, synth.pfn_params(9, 63, seed=5)
+    frames = [synth.dense_tile(n=80_000, seed=70 + i, n_cells=2000 + 500 * i, n_clusters=40) for i in range(3)]
+    voxel_layer = pp.pointpillars.PointPillarsVoxelization("cuda", g["voxel_size"], g["point_cloud_range"], 32, 12000)
+    voxel_encoder = pp.pointpillars.PillarFeatureNet(4, [64], g["voxel_size"], g["point_cloud_range"]).cuda().eval()
+    l = voxel_encoder.pfn_layers[0]
+    with torch.no_grad():
+        l.linear.weight.copy_(cu(pfn["weight"])); l.norm.weight.copy_(cu(pfn["gamma"])); l.norm.bias.copy_(cu(pfn["beta"]))
+        l.norm.running_mean.copy_(cu(pfn["mean"])); l.norm.running_var.copy_(cu(pfn["var"]))
+    pseudoimage_generator = pp.pointpillars.SparseMiddleExtractor([1, 496, 432])
+    with torch.no_grad():
+        voxels, coors, num_points = [], [], []
+        for pc in frames:                                                    # :114-121
+            v, c, n = voxel_layer(pc)
+            voxels.append(v); coors.append(c); num_points.append(n)
+        voxels, num_points = torch.cat(voxels, dim=0), torch.cat(num_points, dim=0)
+        coors = torch.cat([F.pad(c, (1, 0), mode="constant", value=i) for i, c in enumerate(coors)], dim=0)   # :129-132
+        feats = voxel_encoder(voxels, num_points, coors)                     # :98
+        batch_size = coors[-1, 0].item() + 1                                 # :99
+        x = pseudoimage_generator(feats, coors, batch_size)                  # :100
+    assert batch_size == 3 and tuple(x.shape) == (3, 64, 496, 432) and coors.dtype == torch.int64
+    at = 0
+    scale = float(max(np.abs(f[:, :3]).max() for f in frames))
+    for i, pc in enumerate(frames):
+        ov, oc, on = oracle.pointpillars_voxelization(pc, g["voxel_size"], g["point_cloud_range"], 32, 12000)
+        m = len(ov)
+        assert np.array_equal(voxels[at:at + m].cpu().numpy(), ov) and np.array_equal(num_points[at:at + m].cpu().numpy(), on)
+        assert np.array_equal(coors[at:at + m, 1:].cpu().numpy(), oc) and (coors[at:at + m, 0] == i).all()
+        c4 = np.concatenate([np.zeros((m, 1), np.int64), oc], 1)
+        of = oracle.pillar_feature_net(ov, on, c4, [pfn], g["voxel_size"], g["point_cloud_range"])
+        assert_close_t1(feats[at:at + m].cpu().numpy(), of, atol=1e-6 * scale, what="features of frame %d" % i)
+        ref = oracle.scatter_dense(of, c4.astype(np.int32), 1, 1, 496, 432)[0]
+        assert_close_t1(x[i].cpu().numpy(), ref, atol=1e-6 * scale, what="pseudo-image of frame %d" % i)
+        at += m
+    assert at == len(voxels)
+
+
 @pytest.mark.parametrize("order", ["reflectance", "given"])
 def test_frame_pipeline_full_size(pp, oracle, order):
     """BASELINE configs[1] through the preallocated pipeline vs the oracle: the one-call frame (pp_voxelize_scatter), the
@@ -469,3 +549,20 @@ def test_frame_pipeline_full_size(pp, oracle, order):
         pm = pipe.pillar_map.cpu().numpy()
         assert (pm >= 0).sum() == m and np.array_equal(pm[oc[:, 2], oc[:, 1], oc[:, 0]], np.arange(m))
     assert np.array_equal(got == 0, ref == 0) or np.abs(got[(got == 0) != (ref == 0)]).max() < 1e-4
+
+
+@pytest.mark.parametrize("n,k", [(1_920_000, 500), (1_920_000, 4096), (100_000, 20_000), (5000, 5000), (777, 10), (64, 100)])
+def test_head_topk_vs_stable_argsort(pp, n, k):
+    """pp_head_topk = top-nms_pre of the per-anchor scores (model/PointPillars.py:1056-1065) at the reference's
+    400 x 400 x 12 anchor count: indices in descending score, ties by lower index == np.argsort(-s, kind="stable")[:k].
+    Scores are quantised so that ties straddle the k-th place."""
+    rng = np.random.default_rng(n + k)
+    s = (rng.integers(0, 3000, size=n) / 3000.0).astype(np.float32)
+    s[rng.integers(0, n, size=5)] = 1.0
+    got = pp.pointpillars.head_topk(cu(s), k).cpu().numpy()
+    ref = np.argsort(-s, kind="stable")[:min(k, n)]
+    assert got.dtype == np.int64 and np.array_equal(got, ref)
+    # tie-free scores: same indices in the same order as torch.topk
+    s2 = (rng.permutation(n) / float(n)).astype(np.float32)           # tie-free: distinct in float32 for n <= 2^23
+    got2 = pp.pointpillars.head_topk(cu(s2), k)
+    assert torch.equal(got2, cu(s2).topk(min(k, n))[1])
