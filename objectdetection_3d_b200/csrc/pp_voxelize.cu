@@ -21,18 +21,19 @@
 //   S  vox_init_kernel     zero the chunk counters / small counters / histogram, -1 into the hash keys and the
 //                          pillar map; reflectance order: 7 chunk splitters from a 128-key sample (ranked by counting)
 //   A  vox_count_kernel    per point: cell -> slot, chunk(K); ticket = cnt[slot][chunk]++ : the ONE random L2 atomic a
-//                          point costs; per-point record (slot, chunk, ticket, key high word)
+//                          point costs; per-point record (slot, chunk, ticket, key high word).  Extra CTAs rank a
+//                          512-key sample by counting -> 511 fine splitters (ranking bins), off the critical path
 //   B  vox_cells_kernel    per slot: counts -> saturation chunk (the first chunk at which the cell holds max_points
 //                          points), m = points in the chunks up to it; segment of m keys and compact cell id q from
 //                          CTA-wide prefix sums + one atomic per CTA; the counters become write positions
 //                          (segment offset + exclusive prefix over the chunks; "dropped" after the saturation chunk)
 //   C  vox_place_kernel    per point: seg[position[slot][chunk] + ticket] = K -- one cached read and one store, no
 //                          atomic; most points of a dense cell are dropped after the read.  Segments come out ordered
-//                          by chunk.  One extra CTA sorts a 1024-key sample -> 1023 fine splitters (ranking bins)
-//   H  vox_rank_kernel     per cell (thread): smallest key = minimum over the segment's first chunk; ranking bin of
-//                          it (fine splitters + adaptive linear sub-bins), arrival index inside the bin.  The last
-//                          CTA to finish scans the bin histogram, puts the cells in bucket order and settles the
-//                          cutoff when more than max_voxels cells are occupied
+//                          by chunk
+//   H  vox_rank_kernel     per cell (8 lanes): smallest key = minimum over the segment's first chunk; ranking bin of
+//                          it (fine splitters, log-spaced bins), arrival index inside the bin
+//   R  vox_bucket_kernel   every CTA scans the bin histogram in shared memory and puts its cells' first keys in bucket
+//                          order; the last CTA to finish settles the cutoff when more than max_voxels cells are occupied
 //   D  vox_gather_kernel   per cell (warp): pillar id = bucket base + smaller keys inside the bucket; the max_points
 //                          smallest keys of the segment in order (ranks by counting in shared memory; bitonic merges
 //                          for long segments), keys >= cutoff dropped; voxels[pid][s] = points[key.index], coors,
