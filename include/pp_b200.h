@@ -297,7 +297,14 @@ PP_API int pp_assign_overlaps(const float *gt, int64_t G, const float *anchors, 
 PP_API size_t pp_compact_workspace_bytes(int64_t n);
 /* PointPillars.preprocess, model/PointPillars.py:241-266: optional global_outlier_check (ops/ops_numpy.py:111-115:
  * keep |p - mean| < mean(norm) + 5 std(norm)), range filter lo <= xyz < hi (:251-252), feature selection (:266).
- * out (n, n_features) holds *out_count rows in the input order.  range6 and features are HOST arrays. */
+ * out (n, n_features) holds *out_count rows in the input order.  range6 and features are HOST arrays.
+ * outlier_check: PP_OUTLIER_OFF; PP_OUTLIER_EXACT = the statistics in numpy's own float32 order of operations (the
+ * column means as the sequential sums numpy makes of a reduction over the non-contiguous axis, the 1-D reductions
+ * pairwise in blocks of 128): the kept rows are bit-exact with the reference's on float32 input; needs
+ * pp_preprocess_workspace_bytes(n).  PP_OUTLIER_FAST = float64 statistics, fully parallel (pp_compact_workspace_bytes(n)
+ * suffices): rows within rounding of the 5-sigma threshold can differ. */
+enum { PP_OUTLIER_OFF = 0, PP_OUTLIER_EXACT = 1, PP_OUTLIER_FAST = 2 };
+PP_API size_t pp_preprocess_workspace_bytes(int64_t n);
 PP_API int pp_preprocess_points(const float *points, int64_t n, int C, int outlier_check, const float *range6_host,
                          const int32_t *features_host, int n_features, float *out, int32_t *out_count,
                          void *workspace, size_t workspace_bytes, pp_stream_t stream);

@@ -72,6 +72,7 @@ SIGNATURES = {
     "pp_head_topk_workspace_bytes": (_sz, [_i64, _i64]),
     "pp_head_topk": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "pp_compact_workspace_bytes": (_sz, [_i64]),
+    "pp_preprocess_workspace_bytes": (_sz, [_i64]),
     "pp_preprocess_points": (ctypes.c_int, [_vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _sz, _vp]),
     "pp_points_minmax": (ctypes.c_int, [_vp, _i64, ctypes.c_int, _vp, _vp, _sz, _vp]),
     "pp_voxel_centroids": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _vp]),

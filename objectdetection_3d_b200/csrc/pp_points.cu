@@ -105,6 +105,155 @@ norm_stats_kernel(const float *__restrict__ pts, int64_t n, int C, double *sums)
     if ((threadIdx.x & 31) == 0) { atomicAdd(sums + 3, s1); atomicAdd(sums + 4, s2); }
 }
 
+// ---- preprocess: statistics in numpy's own order of operations (exact mode) ------------------------------------------
+// global_outlier_check is float32 numpy code (ops/ops_numpy.py:111-115) and which rows it keeps depends on how numpy
+// rounds its reductions (probed against numpy 2.3, the version the oracle is pinned with):
+//   np.mean(a[:, :3], axis=0)   the reduced axis is not the contiguous one -> numpy adds row after row into one float32
+//                               accumulator per column: a SEQUENTIAL sum (it differs from the pairwise and from the
+//                               float64 result in the 5th digit at 2e5 points)
+//   np.mean / np.std of the 1-D norm array: pairwise summation -- halves (left half rounded down to a multiple of 8)
+//                               down to blocks of <= 128 elements, each summed with 8 interleaved accumulators
+// Both orders are reproduced literally.  The sequential sum is a dependent chain of float adds (three threads, the
+// other threads of the CTA stage the next chunk of points in shared memory); the pairwise tree is walked by one thread
+// while all threads of the CTA sum the leaves.
+constexpr int NPS_THREADS = 1024, NPS_CHUNK = 1024, PW_BLOCK = 128;
+
+__global__ void __launch_bounds__(NPS_THREADS)
+np_colmean3_kernel(const float *__restrict__ pts, int64_t n, int C, float *__restrict__ stats)
+{
+    __shared__ float s_buf[2][3][NPS_CHUNK];
+    const int tid = threadIdx.x;
+    float acc = 0.f;
+    const int64_t chunks = ceil_div(n, NPS_CHUNK);
+    auto stage = [&](int64_t c) {
+        const int64_t i = c * NPS_CHUNK + tid;
+        if (c < chunks && i < n) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s_buf[c & 1][k][tid] = pts[i * C + k];
+        }
+    };
+    stage(0);
+    __syncthreads();
+    for (int64_t c = 0; c < chunks; ++c) {
+        stage(c + 1);
+        if (tid < 3) {
+            const float *col = s_buf[c & 1][tid];
+            const int m = (int)(n - c * NPS_CHUNK < NPS_CHUNK ? n - c * NPS_CHUNK : NPS_CHUNK);
+            int j = 0;
+            for (; j + 8 <= m; j += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = col[j + u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, v[u]);
+            }
+            for (; j < m; ++j) acc = __fadd_rn(acc, col[j]);
+        }
+        __syncthreads();
+    }
+    if (tid < 3) stats[tid] = __fdiv_rn(acc, (float)n);
+}
+
+__device__ __forceinline__ float np_leaf_sum(const float *__restrict__ a, int n)
+{
+    if (n < 8) {
+        float r = 0.f;
+        for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
+        return r;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+}
+
+struct PwFrame { int64_t n; int st; float l; };
+
+// out[0] = numpy's pairwise float32 sum of a[0, n).  One CTA; leaf_start / leaf_val: ceil(n / 64) + 2 entries.
+__global__ void __launch_bounds__(NPS_THREADS)
+np_pairwise_sum_kernel(const float *__restrict__ a, int64_t n, int64_t *__restrict__ leaf_start, float *__restrict__ leaf_val,
+                       float *__restrict__ out)
+{
+    __shared__ int s_leaves;
+    if (threadIdx.x == 0) {
+        // the leaves of the recursion, left to right
+        int64_t stk_s[64], stk_n[64];
+        int sp = 0, L = 0;
+        stk_s[0] = 0; stk_n[0] = n; sp = 1;
+        while (sp) {
+            const int64_t s0 = stk_s[sp - 1], m = stk_n[sp - 1];
+            --sp;
+            if (m <= PW_BLOCK) { leaf_start[L++] = s0; continue; }
+            int64_t n2 = m / 2;
+            n2 -= n2 % 8;
+            stk_s[sp] = s0 + n2; stk_n[sp] = m - n2; ++sp;      // right half: popped after the left one
+            stk_s[sp] = s0; stk_n[sp] = n2; ++sp;
+        }
+        leaf_start[L] = n;
+        s_leaves = L;
+    }
+    __syncthreads();
+    const int L = s_leaves;
+    for (int k = threadIdx.x; k < L; k += NPS_THREADS)
+        leaf_val[k] = np_leaf_sum(a + leaf_start[k], (int)(leaf_start[k + 1] - leaf_start[k]));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // the same recursion again, consuming the leaf sums in order: sum(left) + sum(right)
+        PwFrame stk[64];
+        int sp = 0, next = 0;
+        float ret = 0.f;
+        stk[sp++] = {n, 0, 0.f};
+        while (sp) {
+            PwFrame &f = stk[sp - 1];
+            if (f.st == 0) {
+                if (f.n <= PW_BLOCK) { ret = leaf_val[next++]; --sp; continue; }
+                f.st = 1;
+                int64_t n2 = f.n / 2;
+                n2 -= n2 % 8;
+                stk[sp++] = {n2, 0, 0.f};
+            } else if (f.st == 1) {
+                f.l = ret;
+                f.st = 2;
+                int64_t n2 = f.n / 2;
+                n2 -= n2 % 8;
+                const int64_t rn = f.n - n2;
+                stk[sp++] = {rn, 0, 0.f};
+            } else {
+                ret = __fadd_rn(f.l, ret);
+                --sp;
+            }
+        }
+        out[0] = ret;
+    }
+}
+
+__global__ void __launch_bounds__(PT_THREADS)
+np_norm_kernel(const float *__restrict__ pts, int64_t n, int C, const float *__restrict__ stats, float *__restrict__ norm)
+{
+    const float mean[3] = {stats[0], stats[1], stats[2]};
+    for (int64_t i = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * PT_THREADS)
+        norm[i] = point_norm(pts + i * C, mean);
+}
+
+// np.std's centred squares: x = norm - mean(norm); x * x   (mean(norm) = pairwise sum / n, float32)
+__global__ void __launch_bounds__(PT_THREADS)
+np_sqdev_kernel(const float *__restrict__ norm, int64_t n, float *__restrict__ stats, float *__restrict__ dev)
+{
+    const float m = __fdiv_rn(stats[3], (float)n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[5] = m;
+    for (int64_t i = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * PT_THREADS) {
+        const float x = __fsub_rn(norm[i], m);
+        dev[i] = __fmul_rn(x, x);
+    }
+}
+
 struct Range6 { float lo[3], hi[3]; };
 
 // keep = norm < mean(norm) + 5 std(norm)  (:115)  and  lo <= xyz < hi  (model/PointPillars.py:251-252)
@@ -124,6 +273,22 @@ preprocess_flag_kernel(const float *__restrict__ pts, int64_t n, int C, const do
         const float thr = (float)(m + 5.0 * sqrt(var));
         keep = point_norm(p, mean) < thr;
     }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) keep = keep && p[k] >= rg.lo[k] && p[k] < rg.hi[k];
+    flags[i] = keep ? 1 : 0;
+}
+
+// exact mode: threshold = np.mean(norm) + 5 * np.std(norm) in float32 (numpy 2 scalar rules), norm from the array
+__global__ void __launch_bounds__(PT_THREADS)
+preprocess_flag_exact_kernel(const float *__restrict__ pts, int64_t n, int C, const float *__restrict__ stats,
+                             const float *__restrict__ norm, const Range6 rg, uint8_t *__restrict__ flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const float *p = pts + i * C;
+    const float std_ = __fsqrt_rn(__fdiv_rn(stats[4], (float)n));
+    const float thr = __fadd_rn(stats[5], __fmul_rn(5.f, std_));
+    bool keep = norm[i] < thr;
 #pragma unroll
     for (int k = 0; k < 3; ++k) keep = keep && p[k] >= rg.lo[k] && p[k] < rg.hi[k];
     flags[i] = keep ? 1 : 0;
@@ -227,6 +392,15 @@ extern "C" size_t pp_compact_workspace_bytes(int64_t n)
     return align_up((size_t)(n > 0 ? n : 1)) + align_up((size_t)(ceil_div(n > 0 ? n : 1, PT_THREADS) + 1) * 4) + 256;
 }
 
+extern "C" size_t pp_preprocess_workspace_bytes(int64_t n)
+{
+    if (n < 0) return 0;
+    const size_t n1 = (size_t)(n > 0 ? n : 1), leaves = n1 / 64 + 4;
+    // compaction + (exact statistics) the norm array, the centred squares, the leaves of the pairwise tree
+    return pp_compact_workspace_bytes(n) + 2 * align_up(n1 * sizeof(float)) + align_up(leaves * sizeof(int64_t)) +
+           align_up(leaves * sizeof(float));
+}
+
 namespace {
 struct CompactWs { uint8_t *flags; int32_t *block_base; double *stats; };
 CompactWs carve_compact(void *ws, int64_t n)
@@ -259,18 +433,47 @@ extern "C" int pp_preprocess_points(const float *points, int64_t n, int C, int o
         return PP_ERR_WORKSPACE;
     }
     CompactWs w = carve_compact(workspace, n);
-    if (outlier_check) {
-        PP_CUDA_TRY(cudaMemsetAsync(w.stats, 0, 5 * sizeof(double), st));
-        sum_xyz_kernel<<<stream_grid(n), PT_THREADS, 0, st>>>(points, n, C, w.stats);
-        if (int rc = check_launch("sum_xyz_kernel")) return rc;
-        norm_stats_kernel<<<stream_grid(n), PT_THREADS, 0, st>>>(points, n, C, w.stats);
-        if (int rc = check_launch("norm_stats_kernel")) return rc;
-    }
     Range6 rg;
     for (int k = 0; k < 3; ++k) { rg.lo[k] = range6_host[k]; rg.hi[k] = range6_host[3 + k]; }
     const unsigned nb = (unsigned)ceil_div(n, PT_THREADS);
-    preprocess_flag_kernel<<<nb, PT_THREADS, 0, st>>>(points, n, C, w.stats, outlier_check, rg, w.flags);
-    if (int rc = check_launch("preprocess_flag_kernel")) return rc;
+    if (outlier_check == PP_OUTLIER_EXACT) {
+        // numpy's own order of operations: the kept rows are bit-exact with the reference's (T0)
+        if (workspace_bytes < pp_preprocess_workspace_bytes(n)) {
+            set_error("preprocess workspace too small for the exact statistics (pp_preprocess_workspace_bytes)");
+            return PP_ERR_WORKSPACE;
+        }
+        const size_t n1 = (size_t)n, leaves = n1 / 64 + 4;
+        char *q = (char *)workspace + pp_compact_workspace_bytes(n);
+        float *norm = (float *)q;                       q += align_up(n1 * sizeof(float));
+        float *dev = (float *)q;                        q += align_up(n1 * sizeof(float));
+        int64_t *leaf_start = (int64_t *)q;             q += align_up(leaves * sizeof(int64_t));
+        float *leaf_val = (float *)q;
+        float *fs = (float *)w.stats;                   // [0..2] mean xyz, [3] sum(norm), [4] sum(dev), [5] mean(norm)
+        np_colmean3_kernel<<<1, NPS_THREADS, 0, st>>>(points, n, C, fs);
+        if (int rc = check_launch("np_colmean3_kernel")) return rc;
+        np_norm_kernel<<<stream_grid(n), PT_THREADS, 0, st>>>(points, n, C, fs, norm);
+        if (int rc = check_launch("np_norm_kernel")) return rc;
+        np_pairwise_sum_kernel<<<1, NPS_THREADS, 0, st>>>(norm, n, leaf_start, leaf_val, fs + 3);
+        if (int rc = check_launch("np_pairwise_sum_kernel")) return rc;
+        np_sqdev_kernel<<<stream_grid(n), PT_THREADS, 0, st>>>(norm, n, fs, dev);
+        if (int rc = check_launch("np_sqdev_kernel")) return rc;
+        np_pairwise_sum_kernel<<<1, NPS_THREADS, 0, st>>>(dev, n, leaf_start, leaf_val, fs + 4);
+        if (int rc = check_launch("np_pairwise_sum_kernel")) return rc;
+        preprocess_flag_exact_kernel<<<nb, PT_THREADS, 0, st>>>(points, n, C, fs, norm, rg, w.flags);
+        if (int rc = check_launch("preprocess_flag_exact_kernel")) return rc;
+    } else {
+        if (outlier_check) {
+            // fast statistics: float64 accumulation, fully parallel (kept rows may differ from numpy's by a row or two
+            // per 1e5 points: those within rounding of the 5-sigma threshold)
+            PP_CUDA_TRY(cudaMemsetAsync(w.stats, 0, 5 * sizeof(double), st));
+            sum_xyz_kernel<<<stream_grid(n), PT_THREADS, 0, st>>>(points, n, C, w.stats);
+            if (int rc = check_launch("sum_xyz_kernel")) return rc;
+            norm_stats_kernel<<<stream_grid(n), PT_THREADS, 0, st>>>(points, n, C, w.stats);
+            if (int rc = check_launch("norm_stats_kernel")) return rc;
+        }
+        preprocess_flag_kernel<<<nb, PT_THREADS, 0, st>>>(points, n, C, w.stats, outlier_check, rg, w.flags);
+        if (int rc = check_launch("preprocess_flag_kernel")) return rc;
+    }
     if (int rc = run_compaction_counts(w.flags, n, w.block_base, out_count, st)) return rc;
     FeatSel fs;
     fs.n = n_features;
