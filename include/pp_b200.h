@@ -72,11 +72,12 @@ typedef struct {
 
 enum {
     PP_ORDER_GIVEN = 0,            /* process points in array order (replay of the shuffled order) */
-    PP_ORDER_REFLECTANCE_DESC = 1, /* points[:,3] descending; ties: lower original index first     */
+    PP_ORDER_REFLECTANCE_DESC = 1, /* points[:,3] descending; ties: lower original index first, -0.0 == +0.0 (the reference's
+                                      numba quicksort leaves the order of ties unspecified: replay it with PP_ORDER_PERM) */
     PP_ORDER_PERM = 2              /* caller-supplied permutation: position p reads points[perm[p]] */
 };
 
-/* rows the caller must allocate for voxels/coors/num_points: min(max_voxels, N, cells) */
+/* rows the caller must allocate for voxels/coors/num_points: min(max_voxels, N, cells).  N < 2^27, cells < 2^31. */
 PP_API int64_t pp_voxelize_max_rows(int64_t n_points, const pp_voxel_cfg *cfg);
 PP_API size_t pp_voxelize_workspace_bytes(int64_t n_points, const pp_voxel_cfg *cfg, int order);
 

@@ -43,6 +43,7 @@ def test_frames_shard_without_collectives_on_the_data_path():
     from objectdetection_3d_b200 import sharding
     n_frames, world = 5, 2
     assert sharding.frames_of_rank(8, 1, 4) == [1, 5]
+    assert [sharding.frame_of_rank(k, 1, 4) for k in range(2)] == sharding.frames_of_rank(8, 1, 4)
     assert sorted(sum((sharding.frames_of_rank(n_frames, r, world) for r in range(world)), [])) == list(range(n_frames))
     assert sharding.job_throughput([8, 8], [1.0, 2.0]) == 8.0
     ctx = mp.get_context("spawn")
