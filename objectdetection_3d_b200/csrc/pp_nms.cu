@@ -155,9 +155,6 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
     if (row0 >= n || col0 >= n || col0 + MT_COLS <= row0) return;
     __shared__ float4 s_col[MT_COLS];
     __shared__ uint2 s_colh[MT_COLS];     // the same rectangles as conservative half2 pairs: (x1,y1) down, (x2,y2) up
-    __shared__ float4 s_a0[MODE != PP_NMS_AABB2D ? MT_COLS : 1];       // per-box geometry of the column boxes
-    __shared__ float4 s_a1[MODE != PP_NMS_AABB2D ? MT_COLS : 1];
-    __shared__ float4 s_a2[MODE == PP_NMS_BOX3D ? MT_COLS : 1];
     const int t = threadIdx.x;
 #pragma unroll
     for (int k = 0; k < MT_COLS / MT_ROWS; ++k) {
@@ -166,19 +163,12 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
         const float4 q = c < n ? srect[c] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
         s_col[t + k * MT_ROWS] = q;
         s_colh[t + k * MT_ROWS] = rect_to_half(q);
-        if (MODE != PP_NMS_AABB2D && c < n) {
-            s_a0[t + k * MT_ROWS] = saux.a0[c];
-            s_a1[t + k * MT_ROWS] = saux.a1[c];
-            if (MODE == PP_NMS_BOX3D) s_a2[t + k * MT_ROWS] = saux.a2[c];
-        }
     }
     __syncthreads();
     const int i = row0 + t;
     if (i >= n) return;
     const float4 a = srect[i];
     const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-    typename G::T ga;
-    if (MODE != PP_NMS_AABB2D) ga = G::load(saux.a0, saux.a1, saux.a2, i);
     const uint2 ah = rect_to_half(a);
     const __half2 a_lo = *reinterpret_cast<const __half2 *>(&ah.x), a_hi = *reinterpret_cast<const __half2 *>(&ah.y);
 #pragma unroll 1
@@ -218,14 +208,7 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
             cand &= cand - 1;
             const float4 q = s_col[wd * 64 + j];
             bool hit;
-            if (MODE != PP_NMS_AABB2D) {
-                // same definition as pp_iou_rotated_bev / pp_box3d_overlap: 0 unless the fp32 xy bounding rectangles
-                // overlap, else the clipped-polygon (polyhedron) IoU, symmetric in its arguments
-                if (fminf(a.z, q.z) > fmaxf(a.x, q.x) && fminf(a.w, q.w) > fmaxf(a.y, q.y))
-                    hit = G::exceeds(G::load(s_a0, s_a1, s_a2, wd * 64 + j), ga, thr);
-                else
-                    hit = 0.f > thr;
-            } else if (PREFILTER) {
+            if (PREFILTER) {
                 // iou > thr  <=>  overlap > thr * union, decided without the division unless the two sides are
                 // within 1e-6 relative of each other (then the reference's exact IEEE quotient is evaluated)
                 float w = __fsub_rn(fminf(q.z, a.z), fmaxf(q.x, a.x));
@@ -248,6 +231,119 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
         mask[(size_t)i * nw_stride + cw] = bits;
         // tile-major copy of the diagonal band, streamed by the sweep with one bulk copy per block
         if (kb <= SW_L) band[((size_t)(i >> 6) * (SW_L + 1) + kb) * 64 + (i & 63)] = bits;
+    }
+}
+
+// The clipped pair tests (rotated BEV footprint, oriented 3-D box) cost hundreds to thousands of instructions per pair
+// and only a few percent of the pairs that survive the interval prefilter need them.  Evaluated by the row's own thread
+// (as the rectangle test above is) nearly every exact test would run with one active lane per warp.  Here the CTA works
+// in two phases per 64-column word: (1) every row thread pushes its candidate pairs (interval prefilter, then the fp32
+// rectangle overlap the IoU definition requires) onto a shared-memory queue; (2) all threads pop pairs from the queue
+// and run the exact test with full warps, setting the bits with shared-memory atomics.
+template <bool PREFILTER, int MODE>
+__global__ void __launch_bounds__(MT_ROWS)
+nms_mask_clip_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_cand, float thr, int nw_stride,
+                     u64 *__restrict__ mask, u64 *__restrict__ band, const Aux saux)
+{
+    typedef PairGeom<MODE> G;
+    const int n = *n_cand;
+    const int row0 = blockIdx.y * MT_ROWS, col0 = blockIdx.x * MT_COLS;
+    if (row0 >= n || col0 >= n || col0 + MT_COLS <= row0) return;
+    __shared__ float4 s_col[MT_COLS];
+    __shared__ uint2 s_colh[MT_COLS];
+    __shared__ float4 s_a0[MT_COLS], s_a1[MT_COLS];
+    __shared__ float4 s_a2[MODE == PP_NMS_BOX3D ? MT_COLS : 1];
+    __shared__ float4 s_r0[MT_ROWS], s_r1[MT_ROWS];                   // geometry of the row boxes
+    __shared__ float4 s_r2[MODE == PP_NMS_BOX3D ? MT_ROWS : 1];
+    __shared__ u64 s_bits[MT_ROWS];
+    __shared__ uint16_t s_queue[MT_ROWS * 64];
+    __shared__ int s_count;
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < MT_COLS / MT_ROWS; ++k) {
+        const int c = col0 + t + k * MT_ROWS;
+        const float4 q = c < n ? srect[c] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+        s_col[t + k * MT_ROWS] = q;
+        s_colh[t + k * MT_ROWS] = rect_to_half(q);
+        if (c < n) {
+            s_a0[t + k * MT_ROWS] = saux.a0[c];
+            s_a1[t + k * MT_ROWS] = saux.a1[c];
+            if (MODE == PP_NMS_BOX3D) s_a2[t + k * MT_ROWS] = saux.a2[c];
+        }
+    }
+    const int i = row0 + t;
+    const bool row_ok = i < n;
+    float4 a = make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+    if (row_ok) {
+        a = srect[i];
+        s_r0[t] = saux.a0[i];
+        s_r1[t] = saux.a1[i];
+        if (MODE == PP_NMS_BOX3D) s_r2[t] = saux.a2[i];
+    }
+    if (t == 0) s_count = 0;
+    __syncthreads();
+    const uint2 ah = rect_to_half(a);
+    const __half2 a_lo = *reinterpret_cast<const __half2 *>(&ah.x), a_hi = *reinterpret_cast<const __half2 *>(&ah.y);
+    const bool zero_hits = 0.f > thr;
+#pragma unroll 1
+    for (int wd = 0; wd < MT_COLS / 64; ++wd) {
+        const int c_start = col0 + wd * 64;
+        if (c_start >= n) break;                                      // (uniform over the CTA)
+        const bool needed = row_ok && c_start + 63 >= i;              // words entirely below the diagonal are never read
+        u64 bits = 0;
+        if (needed) {
+            unsigned lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
+            if (PREFILTER) {
+                lo = hi = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint2 qh = s_colh[wd * 64 + j];
+                    const __half2 d1 = __hsub2(*reinterpret_cast<const __half2 *>(&qh.y), a_lo);
+                    const __half2 d2 = __hsub2(a_hi, *reinterpret_cast<const __half2 *>(&qh.x));
+                    const unsigned sg = (*reinterpret_cast<const unsigned *>(&d1) | *reinterpret_cast<const unsigned *>(&d2)) & 0x80008000u;
+                    if (sg == 0) lo |= 1u << j;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint2 qh = s_colh[wd * 64 + 32 + j];
+                    const __half2 d1 = __hsub2(*reinterpret_cast<const __half2 *>(&qh.y), a_lo);
+                    const __half2 d2 = __hsub2(a_hi, *reinterpret_cast<const __half2 *>(&qh.x));
+                    const unsigned sg = (*reinterpret_cast<const unsigned *>(&d1) | *reinterpret_cast<const unsigned *>(&d2)) & 0x80008000u;
+                    if (sg == 0) hi |= 1u << j;
+                }
+            }
+            u64 cand = ((u64)hi << 32) | lo;
+            if (c_start <= i) cand &= ~((2ull << (i - c_start)) - 1ull);      // keep only columns > i
+            if (c_start + 64 > n) cand &= (1ull << (n - c_start)) - 1ull;     // and columns < n
+            while (cand) {
+                const int j = __ffsll((long long)cand) - 1;
+                cand &= cand - 1;
+                const float4 q = s_col[wd * 64 + j];
+                // same definition as pp_iou_rotated_bev / pp_box3d_overlap: 0 unless the fp32 xy bounding rectangles
+                // overlap, else the clipped-polygon (polyhedron) IoU, symmetric in its arguments
+                if (fminf(a.z, q.z) > fmaxf(a.x, q.x) && fminf(a.w, q.w) > fmaxf(a.y, q.y))
+                    s_queue[atomicAdd(&s_count, 1)] = (uint16_t)((t << 6) | j);
+                else if (zero_hits)
+                    bits |= 1ull << j;
+            }
+        }
+        s_bits[t] = bits;
+        __syncthreads();
+        const int cnt = s_count;
+        for (int k = t; k < cnt; k += MT_ROWS) {
+            const int pr = s_queue[k], r = pr >> 6, j = pr & 63;
+            if (G::exceeds(G::load(s_a0, s_a1, s_a2, wd * 64 + j), G::load(s_r0, s_r1, s_r2, r), thr))
+                atomicOr(&s_bits[r], 1ull << j);
+        }
+        __syncthreads();
+        if (t == 0) s_count = 0;
+        if (needed) {
+            const u64 out = s_bits[t];
+            const int cw = c_start >> 6, kb = cw - (i >> 6);
+            mask[(size_t)i * nw_stride + cw] = out;
+            if (kb <= SW_L) band[((size_t)(i >> 6) * (SW_L + 1) + kb) * 64 + (i & 63)] = out;
+        }
+        __syncthreads();
     }
 }
 
@@ -279,6 +375,9 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
     const int n = *n_cand;
     const int nw = (n + 63) >> 6;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef PP_TIMING
+    long long t_start = clock64(), t_loop0 = 0, t_loop1 = 0, t_wait = 0, t_chain = 0;
+#endif
     for (int w = tid; w < nw; w += SWEEP_THREADS) { removed[w] = 0; removed_r[w] = 0; ready[w] = 0; }
     if (tid == 0) {
         s_resolved = 0;
@@ -302,7 +401,13 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
             }
         };
         for (int b = 0; b < SW_RING - 1; ++b) issue_band(b);
+#ifdef PP_TIMING
+        t_loop0 = clock64();
+#endif
         for (int b = 0; b < nw; ++b) {
+#ifdef PP_TIMING
+            const long long tw0 = clock64();
+#endif
             issue_band(b + SW_RING - 1);          // its slot was consumed in step b - 1
             {
                 const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar[b % SW_RING]);
@@ -318,15 +423,32 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
                 while (ready[b] == 0) { }      // pure spin: __nanosleep granularity (~1 us) would dominate the step
             }
             fence_cta();
+#ifdef PP_TIMING
+            const long long tw1 = clock64();
+            t_wait += tw1 - tw0;
+#endif
             const int valid = min(64, n - b * 64);
             u64 alive = ~(*(volatile u64 *)(removed + b) | *(volatile u64 *)(removed_r + b));
             if (valid < 64) alive &= (1ull << valid) - 1;
-            u64 kept = 0;
-            while (alive) {
-                const int i = __ffsll((long long)alive) - 1;
-                kept |= 1ull << i;
-                alive &= ~(slot[i] | (1ull << i));
+            // the chain over the KEPT boxes of the block, on 32-bit halves (one find-first-set + one shared-memory read
+            // per kept box on the dependent path)
+            uint32_t alo = (uint32_t)alive, ahi = (uint32_t)(alive >> 32), klo = 0u, khi = 0u;
+            while (alo) {
+                const int i = __ffs((int)alo) - 1;
+                const u64 row = slot[i];
+                klo |= 1u << i;
+                alo &= ~((uint32_t)row | (1u << i));
+                ahi &= ~(uint32_t)(row >> 32);
             }
+            while (ahi) {
+                const int i = __ffs((int)ahi) - 1;
+                khi |= 1u << i;
+                ahi &= ~((uint32_t)(slot[32 + i] >> 32) | (1u << i));
+            }
+            const u64 kept = ((u64)khi << 32) | klo;
+#ifdef PP_TIMING
+            t_chain += clock64() - tw1;
+#endif
             if (lane == 0) {
                 kept_arr[b] = kept;
                 fence_cta();
@@ -344,6 +466,13 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
             }
             __syncwarp();      // orders the lanes' shared-memory traffic; the slot may be refilled next step
         }
+#ifdef PP_TIMING
+        t_loop1 = clock64();
+        if (lane == 0)
+            printf("sweep n=%d blocks=%d: init %lld | loop %lld cycles = %lld per block (wait %lld, chain %lld)\n", n, nw,
+                   t_loop0 - t_start, t_loop1 - t_loop0, (t_loop1 - t_loop0) / (nw > 0 ? nw : 1), t_wait / (nw > 0 ? nw : 1),
+                   t_chain / (nw > 0 ? nw : 1));
+#endif
     } else {
         // ------------------------------------------------------------------ owners
         const int n_owner = SWEEP_THREADS - 32;
@@ -422,6 +551,9 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
     if (tid == 0) {
         *keep_count = s_base;
         if (kept_n) *kept_n = s_base - base0;
+#ifdef PP_TIMING
+        printf("sweep total %lld cycles\n", clock64() - t_start);
+#endif
     }
 }
 
@@ -529,6 +661,123 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
     }
 }
 
+// The filter for the clipped pair tests, compacted like nms_mask_clip_kernel: per round of FC_CHUNK kept boxes every
+// thread pushes the (box, kept) pairs whose rectangles overlap onto a shared-memory queue, then all threads run the exact
+// tests with full warps.  The ordered compaction of the survivors is the same as in nms_filter_kernel.
+constexpr int FC_CHUNK = 64;
+
+template <int MODE>
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_filter_clip_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__ order, int32_t *__restrict__ sc,
+                       const int32_t *__restrict__ kept_rank, float thr, float4 *__restrict__ srect2,
+                       uint32_t *__restrict__ order2, uint32_t *status, const Aux saux, const Aux saux2)
+{
+    typedef PairGeom<MODE> G;
+    __shared__ float4 s_k[FC_CHUNK], s_k0[FC_CHUNK], s_k1[FC_CHUNK];
+    __shared__ float4 s_k2[MODE == PP_NMS_BOX3D ? FC_CHUNK : 1];
+    __shared__ float4 s_b[FLT_BOXES], s_b0[FLT_BOXES], s_b1[FLT_BOXES];
+    __shared__ float4 s_b2[MODE == PP_NMS_BOX3D ? FLT_BOXES : 1];
+    __shared__ uint16_t s_queue[FLT_BOXES * FC_CHUNK];
+    __shared__ int s_count;
+    __shared__ uint32_t s_tile, s_excl;
+    __shared__ uint32_t s_warp[NMS_THREADS / 32];
+    __shared__ unsigned char s_dead[FLT_BOXES];
+    const int n = sc[SC_N], n1 = sc[SC_N1], k1 = sc[SC_K1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int num_tiles = (n - n1 + FLT_BOXES - 1) / FLT_BOXES;
+    if ((int)blockIdx.x >= num_tiles) return;
+    if (tid == 0) { s_tile = atomicAdd((uint32_t *)&sc[SC_TICKET], 1u); s_count = 0; }
+    if (tid < FLT_BOXES) s_dead[tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tid < FLT_BOXES) {
+        const int r = n1 + (int)tile * FLT_BOXES + tid;
+        if (r < n) {
+            s_b[tid] = srect[r];
+            s_b0[tid] = saux.a0[r];
+            s_b1[tid] = saux.a1[r];
+            if (MODE == PP_NMS_BOX3D) s_b2[tid] = saux.a2[r];
+        } else {
+            s_b[tid] = make_float4(3e38f, 3e38f, -3e38f, -3e38f);
+            s_dead[tid] = 2;                                   // not a box
+        }
+    }
+    const int bi = tid / FLT_SPLIT, part = tid % FLT_SPLIT;
+    const bool zero_hits = 0.f > thr;
+    for (int k0 = 0; k0 < k1; k0 += FC_CHUNK) {
+        if (tid < FC_CHUNK && k0 + tid < k1) {
+            const int kr = kept_rank[k0 + tid];
+            s_k[tid] = srect[kr];
+            s_k0[tid] = saux.a0[kr];
+            s_k1[tid] = saux.a1[kr];
+            if (MODE == PP_NMS_BOX3D) s_k2[tid] = saux.a2[kr];
+        }
+        __syncthreads();
+        const int kn = min(FC_CHUNK, k1 - k0);
+        if (!s_dead[bi]) {
+            const float4 box = s_b[bi];
+            for (int j = part; j < kn; j += FLT_SPLIT) {
+                const float4 q = s_k[j];
+                // empty rectangle intersection -> iou == 0 exactly
+                if (fminf(box.z, q.z) > fmaxf(box.x, q.x) && fminf(box.w, q.w) > fmaxf(box.y, q.y))
+                    s_queue[atomicAdd(&s_count, 1)] = (uint16_t)((bi << 6) | j);
+                else if (zero_hits)
+                    s_dead[bi] = 1;
+            }
+        }
+        __syncthreads();
+        const int cnt = s_count;
+        for (int k = tid; k < cnt; k += NMS_THREADS) {
+            const int pr = s_queue[k], b = pr >> 6, j = pr & 63;
+            if (!s_dead[b] && G::exceeds(G::load(s_b0, s_b1, s_b2, b), G::load(s_k0, s_k1, s_k2, j), thr)) s_dead[b] = 1;
+        }
+        __syncthreads();
+        if (tid == 0) s_count = 0;
+    }
+    __syncthreads();
+    // ordered compaction: block scan of the survivor flags + decoupled look-back over the (ticket-ordered) tiles
+    const bool alive = tid < FLT_BOXES && !s_dead[tid];
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NMS_THREADS / 32; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < warp) wbase += c;
+        total += c;
+    }
+    if (tid == 0) {
+        uint32_t excl = 0;
+        if (tile == 0) {
+            atomicExch(status, FLT_PREFIX | total);
+        } else {
+            atomicExch(status + tile, FLT_AGG | total);
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                const uint32_t v = *((volatile uint32_t *)(status + t));
+                if ((v & FLT_MASK) == 0) continue;
+                excl += v & ~FLT_MASK;
+                if ((v & FLT_MASK) == FLT_PREFIX) break;
+                --t;
+            }
+            atomicExch(status + tile, FLT_PREFIX | (excl + total));
+        }
+        s_excl = excl;
+        if ((int)tile == num_tiles - 1) sc[SC_N2] = (int32_t)(excl + total);
+    }
+    __syncthreads();
+    if (alive) {
+        const int rr = n1 + (int)tile * FLT_BOXES + tid;
+        const uint32_t pos = s_excl + wbase + __popc(bal & lanemask_lt());
+        srect2[pos] = srect[rr];
+        order2[pos] = order[rr];
+        saux2.a0[pos] = saux.a0[rr];
+        saux2.a1[pos] = saux.a1[rr];
+        if (MODE == PP_NMS_BOX3D) saux2.a2[pos] = saux.a2[rr];
+    }
+}
+
 struct NmsWs {
     int32_t *sc;
     uint32_t *status;          // look-back state of the filter's compaction
@@ -587,10 +836,12 @@ int launch_level(const float4 *rects, const int32_t *n_ptr, int64_t n_max, float
     dim3 grid((unsigned)ceil_div(n_max, MT_COLS), (unsigned)ceil_div(n_max, MT_ROWS));
     // thr >= 0: a pair whose bounding rectangles are apart has iou == 0, which only exceeds a negative threshold
 #define PP_MASK(PF, MD) nms_mask_kernel<PF, MD><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, saux)
-    if (mode == PP_NMS_BOX3D) { if (thr >= 0.f) PP_MASK(true, PP_NMS_BOX3D); else PP_MASK(false, PP_NMS_BOX3D); }
-    else if (mode == PP_NMS_ROT_BEV) { if (thr >= 0.f) PP_MASK(true, PP_NMS_ROT_BEV); else PP_MASK(false, PP_NMS_ROT_BEV); }
+#define PP_MASKC(PF, MD) nms_mask_clip_kernel<PF, MD><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, saux)
+    if (mode == PP_NMS_BOX3D) { if (thr >= 0.f) PP_MASKC(true, PP_NMS_BOX3D); else PP_MASKC(false, PP_NMS_BOX3D); }
+    else if (mode == PP_NMS_ROT_BEV) { if (thr >= 0.f) PP_MASKC(true, PP_NMS_ROT_BEV); else PP_MASKC(false, PP_NMS_ROT_BEV); }
     else { if (thr >= 0.f) PP_MASK(true, PP_NMS_AABB2D); else PP_MASK(false, PP_NMS_AABB2D); }
 #undef PP_MASK
+#undef PP_MASKC
     if (int rc = check_launch("nms_mask_kernel")) return rc;
     const size_t smem = ((size_t)SW_RING * SW_BAND + 3 * (size_t)nw) * sizeof(u64) + (size_t)nw * sizeof(int);
     PP_REQUIRE(smem <= 96 * 1024, "too many boxes for the sweep's shared memory");
@@ -654,11 +905,11 @@ extern "C" int pp_nms_mode(const float *boxes9, const float *scores, int64_t sco
     // the other candidates: drop those suppressed by level 1's keep set, compact in rank order, NMS among themselves
     const int64_t l2 = N - NMS_LEVEL1;
     const unsigned fb = (unsigned)ceil_div(l2, FLT_BOXES);
-#define PP_FILTER(MD) nms_filter_kernel<MD><<<fb, NMS_THREADS, 0, st>>>(w.srect, w.order, w.sc, w.kept_rank, iou_thr, w.srect2, \
-                                                                       w.order2, w.status, w.saux, w.saux2)
-    if (iou_mode == PP_NMS_BOX3D) PP_FILTER(PP_NMS_BOX3D);
-    else if (iou_mode == PP_NMS_ROT_BEV) PP_FILTER(PP_NMS_ROT_BEV);
-    else PP_FILTER(PP_NMS_AABB2D);
+#define PP_FILTER(KERNEL, MD) KERNEL<MD><<<fb, NMS_THREADS, 0, st>>>(w.srect, w.order, w.sc, w.kept_rank, iou_thr, w.srect2, \
+                                                                    w.order2, w.status, w.saux, w.saux2)
+    if (iou_mode == PP_NMS_BOX3D) PP_FILTER(nms_filter_clip_kernel, PP_NMS_BOX3D);
+    else if (iou_mode == PP_NMS_ROT_BEV) PP_FILTER(nms_filter_clip_kernel, PP_NMS_ROT_BEV);
+    else PP_FILTER(nms_filter_kernel, PP_NMS_AABB2D);
 #undef PP_FILTER
     if (int rc = check_launch("nms_filter_kernel")) return rc;
     return launch_level(w.srect2, w.sc + SC_N2, l2, iou_thr, w.nw2, w.mask2, w.band2, w.order2, keep, w.sc + SC_K1,
