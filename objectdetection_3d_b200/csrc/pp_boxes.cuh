@@ -195,6 +195,9 @@ __device__ __forceinline__ RRect rrect_pack(const float4 lo, const float2 hi)
 struct Box3 {
     float o[3], e[3][3];
 };
+#ifndef PP_B3_FN
+#define PP_B3_FN __device__ __forceinline__
+#endif
 
 __device__ __forceinline__ Box3 box3_from_corners(const float *c /* (8,3) */)
 {
@@ -265,139 +268,180 @@ __device__ __forceinline__ void dual3(const float e[3][3], float det, float g[3]
     }
 }
 
-constexpr int B3_MAXV = 12;
-// keep lo <= g.q + off <= hi (Sutherland-Hodgman, two passes)
-__device__ __forceinline__ int b3_clip(float (*p)[3], int n, const float g[3], float off, float lo, float hi)
+// ---- exact intersection volume, float64, branch-free ------------------------------------------------------------
+// a is mapped into b's unit-cube frame (cube centre at the origin).  By the divergence theorem the volume is
+//     vol(b) / 3 * ( sum over a's faces  sigma_f det(O_f, E1_f, E2_f) A_f  +  1/2 * sum over the cube's faces A'_f )
+// where A_f is the AREA, in the face's own (u, v) in [0,1]^2 parameters, of the part of the face inside the other box:
+// the unit square cut by three strips  lo <= c0[k] + cu[k] u + cv[k] v <= hi  (one per axis of the other box).  That
+// area is Green's integral of u dv over the boundary, edge by edge: the edge u = 1 and the six strip lines, each cut
+// to the interval the other constraints leave of it.  No polygon is ever built, so there are no loops over vertices,
+// no local arrays and no divergence -- but the two edges that meet in a vertex compute it separately, and the two
+// results must agree far below the size of the face for the contributions to cancel; lines that cross at a shallow
+// angle amplify rounding by 1/sin, so the evaluation is in float64 (half the fp32 issue rate on B200, measured:
+// scripts/micro/fp64_bench.cu), which also makes the result exact to fp32 output precision.
+// Faces of a are cut with closed strips (+eps), faces of the cube with open ones (-eps): coincident faces count once.
+constexpr double B3_EPS = 1e-9;
+
+// 1 / x by two Newton steps on the fp32 reciprocal; +-inf for |x| < 1e-30 (lines taken as parallel)
+PP_B3_FN bool b3_tiny(double x) { return fabsf((float)x) < 1e-30f; }
+PP_B3_FN double b3_rcp(double x)
 {
-    float q[B3_MAXV][3], s[B3_MAXV];
-#pragma unroll 1
-    for (int pass = 0; pass < 2 && n > 0; ++pass) {
-        const float sgn = pass ? -1.f : 1.f, lim = pass ? -hi : lo;
-        for (int i = 0; i < n; ++i) s[i] = sgn * (g[0] * p[i][0] + g[1] * p[i][1] + g[2] * p[i][2] + off) - lim;
-        int m = 0;
-        for (int i = 0; i < n; ++i) {
-            const int j = (i + 1 == n) ? 0 : i + 1;
-            // (a convex polygon clipped by a slab gains at most two vertices; the bound check is for inputs whose signs
-            // alternate through rounding on near-degenerate, co-planar faces)
-            if (s[i] >= 0.f && m < B3_MAXV) { q[m][0] = p[i][0]; q[m][1] = p[i][1]; q[m][2] = p[i][2]; ++m; }
-            if (((s[i] > 0.f && s[j] < 0.f) || (s[i] < 0.f && s[j] > 0.f)) && m < B3_MAXV) {
-                const float t = s[i] / (s[i] - s[j]);
-                q[m][0] = p[i][0] + t * (p[j][0] - p[i][0]);
-                q[m][1] = p[i][1] + t * (p[j][1] - p[i][1]);
-                q[m][2] = p[i][2] + t * (p[j][2] - p[i][2]);
-                ++m;
-            }
-        }
-        n = m;
-        for (int i = 0; i < n; ++i) { p[i][0] = q[i][0]; p[i][1] = q[i][1]; p[i][2] = q[i][2]; }
+    const float xf = (float)x;
+#ifdef __CUDA_ARCH__
+    const float rf = __frcp_rn(xf);
+#else
+    const float rf = 1.0f / xf;
+#endif
+    double r = (double)rf;
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    const double inf = x < 0.0 ? -(double)INFINITY : (double)INFINITY;
+    return b3_tiny(x) ? inf : r;
+}
+// [tmin, tmax] &= { t : lo <= f0 + t / r <= hi }   (r = 1 / slope, +-inf when the slope is 0)
+PP_B3_FN void b3_cut(double &tmin, double &tmax, double f0, double r, bool pos, double lo, double hi)
+{
+    const double t1 = (lo - f0) * r, t2 = (hi - f0) * r;
+    const double a = pos ? t1 : t2, b = pos ? t2 : t1;
+    tmin = a > tmin ? a : tmin;          // (a NaN -- a bound that coincides with a parallel line -- leaves the interval as it is)
+    tmax = b < tmax ? b : tmax;
+}
+// what the three strips share between the two opposite faces of one axis
+struct B3Lines {
+    double cu[3], cv[3];      // strip k: c0[k] + cu[k] u + cv[k] v
+    double rcu[3], rcv[3];    // 1 / cu, 1 / cv
+    double rnn[3];            // 1 / (cu^2 + cv^2); 0 for a strip that does not depend on (u, v)
+    double rx[3];             // 1 / (cu[j] cv[k] - cv[j] cu[k]) for (j, k) = (1, 2), (2, 0), (0, 1)
+};
+PP_B3_FN void b3_lines(B3Lines &L)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        L.rcu[k] = b3_rcp(L.cu[k]);
+        L.rcv[k] = b3_rcp(L.cv[k]);
+        const double nn = L.cu[k] * L.cu[k] + L.cv[k] * L.cv[k];
+        const double r = b3_rcp(nn);
+        L.rnn[k] = b3_tiny(nn) ? 0.0 : r;
+        const int j = (k + 1) % 3, m = (k + 2) % 3;
+        L.rx[k] = b3_rcp(L.cu[j] * L.cv[m] - L.cv[j] * L.cu[m]);
     }
-    return n;
 }
-// 6 x signed volume of the cone from the origin over the polygon
-__device__ __forceinline__ float b3_cone(float (*p)[3], int n)
+// area of { (u, v) in [0,1]^2 : lo <= c0[k] + cu[k] u + cv[k] v <= hi, k = 0..2 }
+PP_B3_FN double b3_area(const B3Lines &L, const double c0[3], double lo, double hi)
 {
-    float v = 0.f;
-    for (int i = 1; i + 1 < n; ++i) v += det3(p[0], p[i], p[i + 1]);
-    return v;
+    // edge u = 1, parameter v
+    double tmin = 0.0, tmax = 1.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) b3_cut(tmin, tmax, c0[k] + L.cu[k], L.rcv[k], L.rcv[k] >= 0.0, lo, hi);
+    double area = tmax > tmin ? tmax - tmin : 0.0;
+    // strip lines: P + t D with D = (cv, -cu); the interior is on the left of D for the lo line, on the right for hi
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int j = (k + 1) % 3, m = (k + 2) % 3;
+        const double du = L.cv[k], dv = -L.cu[k];
+        // reciprocal slopes of the other constraints along D: u: 1 / du, v: 1 / dv, strip j: 1 / (cu[j] du + cv[j] dv)
+        const double r_u = L.rcv[k], r_v = -L.rcu[k];
+        const double r_j = -L.rx[m], r_m = L.rx[j];       // 1 / (cu[j] cv[k] - cv[j] cu[k]),  1 / (cu[m] cv[k] - cv[m] cu[k])
+        const bool p_u = r_u >= 0.0, p_v = r_v >= 0.0, p_j = r_j >= 0.0, p_m = r_m >= 0.0;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const double sc = ((side ? hi : lo) - c0[k]) * L.rnn[k];
+            const double pu = L.cu[k] * sc, pv = L.cv[k] * sc;
+            double t0 = -1e300, t1 = 1e300;
+            b3_cut(t0, t1, pu, r_u, p_u, 0.0, 1.0);
+            b3_cut(t0, t1, pv, r_v, p_v, 0.0, 1.0);
+            b3_cut(t0, t1, c0[j] + L.cu[j] * pu + L.cv[j] * pv, r_j, p_j, lo, hi);
+            b3_cut(t0, t1, c0[m] + L.cu[m] * pu + L.cv[m] * pv, r_m, p_m, lo, hi);
+            const double c = 0.5 * (2.0 * pu + (t0 + t1) * du) * ((t1 - t0) * dv);
+            const bool ok = t1 > t0 && L.rnn[k] != 0.0;
+            area += ok ? (side ? -c : c) : 0.0;
+        }
+    }
+    return area;
 }
-// face f = 2 * axis + side of the parallelepiped (o; e), outward orientation for a right-handed basis
-__device__ __forceinline__ void b3_face(const float o[3], const float e[3][3], int f, float (*p)[3])
+
+PP_B3_FN double det3d(const double a[3], const double b[3], const double c[3])
 {
-    const int ax = f >> 1, side = f & 1, a = (ax + 1) % 3, b = (ax + 2) % 3;
+    return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+}
+// rows of the inverse of the matrix whose columns are e[0], e[1], e[2]
+PP_B3_FN void dual3d(const double e[3][3], double det, double g[3][3])
+{
+    const double r = 1.0 / det;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int k = side ? i : 3 - i;
-        const float ua = (k == 1 || k == 2) ? 1.f : 0.f, ub = (k >= 2) ? 1.f : 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) p[i][c] = o[c] + (side ? e[ax][c] : 0.f) + ua * e[a][c] + ub * e[b][c];
+    for (int k = 0; k < 3; ++k) {
+        const double *a = e[(k + 1) % 3], *b = e[(k + 2) % 3];
+        g[k][0] = (a[1] * b[2] - a[2] * b[1]) * r;
+        g[k][1] = (a[2] * b[0] - a[0] * b[2]) * r;
+        g[k][2] = (a[0] * b[1] - a[1] * b[0]) * r;
     }
 }
 
-// Volume of a ∩ b: a is mapped into b's unit-cube frame (cube centre at the origin); the volume is the sum of the
-// cones over a's faces clipped to the cube (closed slabs) and the cube's faces clipped to a (open slabs).
-__device__ __forceinline__ float box3_inter_volume(const Box3 &a, const Box3 &b, float &va, float &vb)
+PP_B3_FN double box3_inter_volume(const Box3 &a, const Box3 &b, double &va, double &vb)
 {
-    const float eps = 1e-6f;
-    const float d1 = det3(a.e[0], a.e[1], a.e[2]), d2 = det3(b.e[0], b.e[1], b.e[2]);
-    va = fabsf(d1); vb = fabsf(d2);
-    if (!(va > 0.f) || !(vb > 0.f)) return 0.f;
-    float g2[3][3];
-    dual3(b.e, d2, g2);
-    float po[3], pe[3][3];
-    const float dx = a.o[0] - b.o[0], dy = a.o[1] - b.o[1], dz = a.o[2] - b.o[2];
+    double ae[3][3], be[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { ae[k][c] = (double)a.e[k][c]; be[k][c] = (double)b.e[k][c]; }
+    const double d1 = det3d(ae[0], ae[1], ae[2]), d2 = det3d(be[0], be[1], be[2]);
+    va = fabs(d1); vb = fabs(d2);
+    if (!(va > 0.0) || !(vb > 0.0)) return 0.0;
+    double g2[3][3];
+    dual3d(be, d2, g2);
+    // org[0] / mat[0]: a in b's frame (origin po, edges pe[k]); org[1] / mat[1]: the cube in a's frame (the image of
+    // the corner (-1/2,-1/2,-1/2) and of the unit steps along b's axes) -- the same shape, so one loop body serves both
+    double org[2][3], mat[2][3][3];
+    const double dx = (double)a.o[0] - (double)b.o[0], dy = (double)a.o[1] - (double)b.o[1], dz = (double)a.o[2] - (double)b.o[2];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        po[r] = g2[r][0] * dx + g2[r][1] * dy + g2[r][2] * dz - 0.5f;
+        org[0][r] = g2[r][0] * dx + g2[r][1] * dy + g2[r][2] * dz - 0.5;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) pe[k][r] = g2[r][0] * a.e[k][0] + g2[r][1] * a.e[k][1] + g2[r][2] * a.e[k][2];
+        for (int k = 0; k < 3; ++k) mat[0][k][r] = g2[r][0] * ae[k][0] + g2[r][1] * ae[k][1] + g2[r][2] * ae[k][2];
     }
     // quick reject: the image of a lies entirely beyond one side of the cube
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const float lo = po[r] + fminf(pe[0][r], 0.f) + fminf(pe[1][r], 0.f) + fminf(pe[2][r], 0.f);
-        const float hi = po[r] + fmaxf(pe[0][r], 0.f) + fmaxf(pe[1][r], 0.f) + fmaxf(pe[2][r], 0.f);
-        if (lo >= 0.5f || hi <= -0.5f) return 0.f;
+        const double lo = org[0][r] + fmin(mat[0][0][r], 0.0) + fmin(mat[0][1][r], 0.0) + fmin(mat[0][2][r], 0.0);
+        const double hi = org[0][r] + fmax(mat[0][0][r], 0.0) + fmax(mat[0][1][r], 0.0) + fmax(mat[0][2][r], 0.0);
+        if (lo >= 0.5 || hi <= -0.5) return 0.0;
     }
-    const float dp = det3(pe[0], pe[1], pe[2]);
-    float gp[3][3];
-    dual3(pe, dp, gp);
-    float sum_p = 0.f, sum_c = 0.f, poly[B3_MAXV][3];
-    const float ax[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
-    // Per face: the slab coordinates of its four vertices decide most cases without clipping -- all four beyond the
-    // same side of a slab: the face contributes nothing; all four inside every slab: its cone as it is; only faces
-    // that straddle a slab boundary go through Sutherland-Hodgman, and only against the slabs they straddle.
+    const double dp = det3d(mat[0][0], mat[0][1], mat[0][2]);
+    double gp[3][3];
+    dual3d(mat[0], dp, gp);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double off = -(gp[k][0] * org[0][0] + gp[k][1] * org[0][1] + gp[k][2] * org[0][2]);
+        org[1][k] = off - 0.5 * (gp[k][0] + gp[k][1] + gp[k][2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) mat[1][c][k] = gp[k][c];
+    }
+    const double sg = dp < 0.0 ? -1.0 : 1.0;
+    double sum = 0.0;
 #pragma unroll 1
-    for (int f = 0; f < 6; ++f) {
-        b3_face(po, pe, f, poly);
-        unsigned all_out = ~0u, any_out = 0u;
+    for (int task = 0; task < 6; ++task) {
+        const int which = task >= 3 ? 1 : 0, ax = task - 3 * which;
+        const int ia = ax == 2 ? 0 : ax + 1, ib = ax == 0 ? 2 : ax - 1;
+        B3Lines L;
+        double c0a[3], c0b[3];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            unsigned oc = 0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                oc |= (poly[i][k] < -0.5f - eps) ? (1u << (2 * k)) : 0u;
-                oc |= (poly[i][k] > 0.5f + eps) ? (2u << (2 * k)) : 0u;
-            }
-            all_out &= oc;
-            any_out |= oc;
+        for (int k = 0; k < 3; ++k) {
+            c0a[k] = org[which][k];
+            c0b[k] = org[which][k] + mat[which][ax][k];
+            L.cu[k] = mat[which][ia][k];
+            L.cv[k] = mat[which][ib][k];
         }
-        if (all_out & 0x3Fu) continue;
-        int n = 4;
-#pragma unroll 1
-        for (int k = 0; k < 3 && n > 2; ++k)
-            if ((any_out >> (2 * k)) & 3u) n = b3_clip(poly, n, ax[k], 0.f, -0.5f - eps, 0.5f + eps);
-        if (n > 2) sum_p += b3_cone(poly, n);
+        b3_lines(L);
+        const double lo = which ? B3_EPS : -0.5 - B3_EPS, hi = which ? 1.0 - B3_EPS : 0.5 + B3_EPS;
+        const double a0 = b3_area(L, c0a, lo, hi), a1 = b3_area(L, c0b, lo, hi);
+        // cone weights: a's faces sigma * det(O, E1, E2) = -h0 (low side), h0 + dp (high side), times sign(dp);
+        // the cube's faces are at distance 1/2 from the apex
+        const double h0 = det3d(c0a, mat[0][ia], mat[0][ib]);
+        sum += which ? 0.5 * (a0 + a1) : sg * ((h0 + dp) * a1 - h0 * a0);
     }
-    const float co[3] = {-0.5f, -0.5f, -0.5f};
-    float offk[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) offk[k] = -(gp[k][0] * po[0] + gp[k][1] * po[1] + gp[k][2] * po[2]);
-#pragma unroll 1
-    for (int f = 0; f < 6; ++f) {
-        b3_face(co, ax, f, poly);
-        unsigned all_out = ~0u, any_out = 0u;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            unsigned oc = 0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float sk = gp[k][0] * poly[i][0] + gp[k][1] * poly[i][1] + gp[k][2] * poly[i][2] + offk[k];
-                oc |= (sk < eps) ? (1u << (2 * k)) : 0u;
-                oc |= (sk > 1.f - eps) ? (2u << (2 * k)) : 0u;
-            }
-            all_out &= oc;
-            any_out |= oc;
-        }
-        if (all_out & 0x3Fu) continue;
-        int n = 4;
-#pragma unroll 1
-        for (int k = 0; k < 3 && n > 2; ++k)
-            if ((any_out >> (2 * k)) & 3u) n = b3_clip(poly, n, gp[k], offk[k], eps, 1.f - eps);
-        if (n > 2) sum_c += b3_cone(poly, n);
-    }
-    float v = ((dp < 0.f ? -sum_p : sum_p) + sum_c) * (1.f / 6.f) * vb;
-    v = fmaxf(v, 0.f);
-    return fminf(v, fminf(va, vb));
+    double v = sum * (1.0 / 3.0) * vb;
+    v = fmax(v, 0.0);
+    return fmin(v, fmin(va, vb));
 }
 
 // Image of a in b's unit frame, axis by axis: false when an axis of b separates the boxes; else ub = vol(b) x the
@@ -430,17 +474,18 @@ __device__ __forceinline__ bool box3_proj_bound(const Box3 &a, const Box3 &b, fl
 }
 
 // Symmetric by construction (canonical argument order), like rrect_iou.
-__device__ __forceinline__ float box3_iou(const Box3 &a, const Box3 &b, float *vol_out)
+PP_B3_FN float box3_iou(const Box3 &a, const Box3 &b, float *vol_out)
 {
     bool swap = false;
 #pragma unroll
     for (int k = 2; k >= 0; --k)
         if (a.o[k] != b.o[k]) swap = a.o[k] > b.o[k];
-    float va, vb;
-    const float v = swap ? box3_inter_volume(b, a, vb, va) : box3_inter_volume(a, b, va, vb);
-    if (vol_out) *vol_out = v;
-    const float u = (swap ? vb + va : va + vb) - v;
-    return u > 0.f ? v / u : 0.f;
+    const Box3 &p = swap ? b : a, &q = swap ? a : b;      // one instance of the volume code
+    double vp, vq;
+    const double v = box3_inter_volume(p, q, vp, vq);
+    if (vol_out) *vol_out = (float)v;
+    const double u = vp + vq - v;
+    return u > 0.0 ? (float)(v / u) : 0.f;
 }
 
 }  // namespace pp

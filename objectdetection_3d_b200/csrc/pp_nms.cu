@@ -41,7 +41,8 @@ template <> struct PairGeom<PP_NMS_ROT_BEV> {
         const float4 h = a1[i];
         return rrect_pack(a0[i], make_float2(h.x, h.y));
     }
-    static __device__ __forceinline__ float iou(const T &a, const T &b) { return rrect_iou(a, b); }
+    static __device__ __forceinline__ bool maybe(const T &, const T &, float) { return true; }
+    static __device__ __forceinline__ bool exact(const T &a, const T &b, float thr) { return rrect_iou(a, b) > thr; }
     static __device__ __forceinline__ bool exceeds(const T &a, const T &b, float thr) { return rrect_iou(a, b) > thr; }
 };
 template <> struct PairGeom<PP_NMS_BOX3D> {
@@ -50,24 +51,22 @@ template <> struct PairGeom<PP_NMS_BOX3D> {
     {
         return box3_load(a0[i], a1[i], a2[i]);
     }
-    static __device__ __forceinline__ float iou(const T &a, const T &b) { return box3_iou(a, b, nullptr); }
-    // iou > thr?  Most pairs are decided without clipping: an axis of either box separates them, or the intersection,
-    // which lies inside box b and inside the b-aligned bounding box of a (and vice versa), is too small to reach the
-    // threshold (iou is increasing in the volume; the bound is inflated by 1e-3 relative, far above the fp32 error of
-    // the clipped volume).
-    static __device__ __forceinline__ bool exceeds(const T &a, const T &b, float thr)
+    // Can iou exceed thr at all?  Most pairs are decided here, in fp32: an axis of either box separates them (the
+    // intersection is empty and 0 > thr is false), or the intersection, which lies inside box b and inside the
+    // b-aligned bounding box of a (and vice versa), is too small to reach the threshold (iou is increasing in the
+    // volume; the bound is inflated by 1e-3 relative, far above its fp32 error).
+    static __device__ __forceinline__ bool maybe(const T &a, const T &b, float thr)
     {
-        if (thr >= 0.f) {
-            // separating axes of either box: no intersection (box3_iou returns 0 for these, and 0 > thr is false)
-            float ub1, ub2;
-            if (!box3_proj_bound(a, b, ub1) || !box3_proj_bound(b, a, ub2)) return false;
-            const float ub = fminf(ub1, ub2) * 1.001f;
-            const float va = fabsf(det3(a.e[0], a.e[1], a.e[2])), vb = fabsf(det3(b.e[0], b.e[1], b.e[2]));
-            // iou(ub) = ub / (va + vb - ub) <= thr  <=>  ub * (1 + thr) <= thr * (va + vb)
-            if (ub * (1.f + thr) <= thr * (va + vb)) return false;
-        }
-        return box3_iou(a, b, nullptr) > thr;
+        if (thr < 0.f) return true;
+        float ub1, ub2;
+        if (!box3_proj_bound(a, b, ub1) || !box3_proj_bound(b, a, ub2)) return false;
+        const float ub = fminf(ub1, ub2) * 1.001f;
+        const float va = fabsf(det3(a.e[0], a.e[1], a.e[2])), vb = fabsf(det3(b.e[0], b.e[1], b.e[2]));
+        // iou(ub) = ub / (va + vb - ub) <= thr  <=>  ub * (1 + thr) <= thr * (va + vb)
+        return !(ub * (1.f + thr) <= thr * (va + vb));
     }
+    static __device__ __forceinline__ bool exact(const T &a, const T &b, float thr) { return box3_iou(a, b, nullptr) > thr; }
+    static __device__ __forceinline__ bool exceeds(const T &a, const T &b, float thr) { return maybe(a, b, thr) && exact(a, b, thr); }
 };
 
 __global__ void __launch_bounds__(NMS_THREADS)
@@ -236,12 +235,27 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
 
 // The clipped pair tests (rotated BEV footprint, oriented 3-D box) cost hundreds to thousands of instructions per pair
 // and only a few percent of the pairs that survive the interval prefilter need them.  Evaluated by the row's own thread
-// (as the rectangle test above is) nearly every exact test would run with one active lane per warp.  Here the CTA works
-// in two phases per 64-column word: (1) every row thread pushes its candidate pairs (interval prefilter, then the fp32
-// rectangle overlap the IoU definition requires) onto a shared-memory queue; (2) all threads pop pairs from the queue
-// and run the exact test with full warps, setting the bits with shared-memory atomics.
+// (as the rectangle test above is) nearly every exact test would run with one active lane per warp -- and even a queue
+// per 64-column word fills three lanes of a warp on average (ncu, 20k boxes).  So the CTA keeps two queues in shared
+// memory for its whole 128 x 256 tile: (1) every row thread pushes the pairs whose rectangles overlap (interval
+// prefilter, then the fp32 rectangle overlap the IoU definition requires); (2) all threads pop those, run the cheap
+// conservative test of the mode (PairGeom::maybe) and push the pairs it cannot decide onto the second queue; (3) when
+// that one is nearly full, and at the end of the tile, all threads pop it and run the exact test with full warps,
+// setting the mask bits with shared-memory atomics.
+constexpr int MC_Q1 = 12288;       // entries of the first queue; a 64-column word adds at most 128 x 64
+constexpr int MC_Q2 = 2048;        // entries of the second
+template <int MODE> struct ClipSmem {
+    float4 col[MT_COLS];
+    uint2 colh[MT_COLS];
+    float4 a0[MT_COLS], a1[MT_COLS], a2[MODE == PP_NMS_BOX3D ? MT_COLS : 1];       // geometry of the column boxes
+    float4 r0[MT_ROWS], r1[MT_ROWS], r2[MODE == PP_NMS_BOX3D ? MT_ROWS : 1];       // and of the row boxes
+    u64 bits[MT_COLS / 64][MT_ROWS];
+    uint16_t q1[MC_Q1], q2[MC_Q2];
+    int n1, n2;
+};
+
 template <bool PREFILTER, int MODE>
-__global__ void __launch_bounds__(MT_ROWS)
+__global__ void __launch_bounds__(MT_ROWS, 3)
 nms_mask_clip_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_cand, float thr, int nw_stride,
                      u64 *__restrict__ mask, u64 *__restrict__ band, const Aux saux)
 {
@@ -249,26 +263,19 @@ nms_mask_clip_kernel(const float4 *__restrict__ srect, const int32_t *__restrict
     const int n = *n_cand;
     const int row0 = blockIdx.y * MT_ROWS, col0 = blockIdx.x * MT_COLS;
     if (row0 >= n || col0 >= n || col0 + MT_COLS <= row0) return;
-    __shared__ float4 s_col[MT_COLS];
-    __shared__ uint2 s_colh[MT_COLS];
-    __shared__ float4 s_a0[MT_COLS], s_a1[MT_COLS];
-    __shared__ float4 s_a2[MODE == PP_NMS_BOX3D ? MT_COLS : 1];
-    __shared__ float4 s_r0[MT_ROWS], s_r1[MT_ROWS];                   // geometry of the row boxes
-    __shared__ float4 s_r2[MODE == PP_NMS_BOX3D ? MT_ROWS : 1];
-    __shared__ u64 s_bits[MT_ROWS];
-    __shared__ uint16_t s_queue[MT_ROWS * 64];
-    __shared__ int s_count;
+    extern __shared__ __align__(16) unsigned char clip_smem[];
+    ClipSmem<MODE> &S = *reinterpret_cast<ClipSmem<MODE> *>(clip_smem);
     const int t = threadIdx.x;
 #pragma unroll
     for (int k = 0; k < MT_COLS / MT_ROWS; ++k) {
         const int c = col0 + t + k * MT_ROWS;
         const float4 q = c < n ? srect[c] : make_float4(3e38f, 3e38f, -3e38f, -3e38f);
-        s_col[t + k * MT_ROWS] = q;
-        s_colh[t + k * MT_ROWS] = rect_to_half(q);
+        S.col[t + k * MT_ROWS] = q;
+        S.colh[t + k * MT_ROWS] = rect_to_half(q);
         if (c < n) {
-            s_a0[t + k * MT_ROWS] = saux.a0[c];
-            s_a1[t + k * MT_ROWS] = saux.a1[c];
-            if (MODE == PP_NMS_BOX3D) s_a2[t + k * MT_ROWS] = saux.a2[c];
+            S.a0[t + k * MT_ROWS] = saux.a0[c];
+            S.a1[t + k * MT_ROWS] = saux.a1[c];
+            if (MODE == PP_NMS_BOX3D) S.a2[t + k * MT_ROWS] = saux.a2[c];
         }
     }
     const int i = row0 + t;
@@ -276,74 +283,110 @@ nms_mask_clip_kernel(const float4 *__restrict__ srect, const int32_t *__restrict
     float4 a = make_float4(3e38f, 3e38f, -3e38f, -3e38f);
     if (row_ok) {
         a = srect[i];
-        s_r0[t] = saux.a0[i];
-        s_r1[t] = saux.a1[i];
-        if (MODE == PP_NMS_BOX3D) s_r2[t] = saux.a2[i];
+        S.r0[t] = saux.a0[i];
+        S.r1[t] = saux.a1[i];
+        if (MODE == PP_NMS_BOX3D) S.r2[t] = saux.a2[i];
     }
-    if (t == 0) s_count = 0;
+    if (t == 0) { S.n1 = 0; S.n2 = 0; }
     __syncthreads();
     const uint2 ah = rect_to_half(a);
     const __half2 a_lo = *reinterpret_cast<const __half2 *>(&ah.x), a_hi = *reinterpret_cast<const __half2 *>(&ah.y);
     const bool zero_hits = 0.f > thr;
+    int wd = 0;
+    bool filling = true;
+    // one loop, one copy of each test in the code: fill the first queue word by word; drain it when the next word
+    // might not fit, and after the last word
 #pragma unroll 1
-    for (int wd = 0; wd < MT_COLS / 64; ++wd) {
-        const int c_start = col0 + wd * 64;
-        if (c_start >= n) break;                                      // (uniform over the CTA)
-        const bool needed = row_ok && c_start + 63 >= i;              // words entirely below the diagonal are never read
-        u64 bits = 0;
-        if (needed) {
-            unsigned lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
-            if (PREFILTER) {
-                lo = hi = 0;
+    while (true) {
+        if (filling) {
+            const int c_start = col0 + wd * 64;
+            u64 bits = 0;
+            if (row_ok && c_start < n && c_start + 63 >= i) {         // words entirely below the diagonal are never read
+                unsigned lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
+                if (PREFILTER) {
+                    lo = hi = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const uint2 qh = s_colh[wd * 64 + j];
-                    const __half2 d1 = __hsub2(*reinterpret_cast<const __half2 *>(&qh.y), a_lo);
-                    const __half2 d2 = __hsub2(a_hi, *reinterpret_cast<const __half2 *>(&qh.x));
-                    const unsigned sg = (*reinterpret_cast<const unsigned *>(&d1) | *reinterpret_cast<const unsigned *>(&d2)) & 0x80008000u;
-                    if (sg == 0) lo |= 1u << j;
+                    for (int j = 0; j < 32; ++j) {
+                        const uint2 qh = S.colh[wd * 64 + j];
+                        const __half2 d1 = __hsub2(*reinterpret_cast<const __half2 *>(&qh.y), a_lo);
+                        const __half2 d2 = __hsub2(a_hi, *reinterpret_cast<const __half2 *>(&qh.x));
+                        const unsigned sg = (*reinterpret_cast<const unsigned *>(&d1) | *reinterpret_cast<const unsigned *>(&d2)) & 0x80008000u;
+                        if (sg == 0) lo |= 1u << j;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const uint2 qh = S.colh[wd * 64 + 32 + j];
+                        const __half2 d1 = __hsub2(*reinterpret_cast<const __half2 *>(&qh.y), a_lo);
+                        const __half2 d2 = __hsub2(a_hi, *reinterpret_cast<const __half2 *>(&qh.x));
+                        const unsigned sg = (*reinterpret_cast<const unsigned *>(&d1) | *reinterpret_cast<const unsigned *>(&d2)) & 0x80008000u;
+                        if (sg == 0) hi |= 1u << j;
+                    }
                 }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const uint2 qh = s_colh[wd * 64 + 32 + j];
-                    const __half2 d1 = __hsub2(*reinterpret_cast<const __half2 *>(&qh.y), a_lo);
-                    const __half2 d2 = __hsub2(a_hi, *reinterpret_cast<const __half2 *>(&qh.x));
-                    const unsigned sg = (*reinterpret_cast<const unsigned *>(&d1) | *reinterpret_cast<const unsigned *>(&d2)) & 0x80008000u;
-                    if (sg == 0) hi |= 1u << j;
+                u64 cand = ((u64)hi << 32) | lo;
+                if (c_start <= i) cand &= ~((2ull << (i - c_start)) - 1ull);      // keep only columns > i
+                if (c_start + 64 > n) cand &= (1ull << (n - c_start)) - 1ull;     // and columns < n
+                while (cand) {
+                    const int j = __ffsll((long long)cand) - 1;
+                    cand &= cand - 1;
+                    const float4 q = S.col[wd * 64 + j];
+                    // same definition as pp_iou_rotated_bev / pp_box3d_overlap: 0 unless the fp32 xy bounding rectangles
+                    // overlap, else the clipped-polygon (polyhedron) IoU, symmetric in its arguments
+                    if (fminf(a.z, q.z) > fmaxf(a.x, q.x) && fminf(a.w, q.w) > fmaxf(a.y, q.y))
+                        S.q1[atomicAdd(&S.n1, 1)] = (uint16_t)((t << 8) | (wd * 64 + j));
+                    else if (zero_hits)
+                        bits |= 1ull << j;
                 }
             }
-            u64 cand = ((u64)hi << 32) | lo;
-            if (c_start <= i) cand &= ~((2ull << (i - c_start)) - 1ull);      // keep only columns > i
-            if (c_start + 64 > n) cand &= (1ull << (n - c_start)) - 1ull;     // and columns < n
-            while (cand) {
-                const int j = __ffsll((long long)cand) - 1;
-                cand &= cand - 1;
-                const float4 q = s_col[wd * 64 + j];
-                // same definition as pp_iou_rotated_bev / pp_box3d_overlap: 0 unless the fp32 xy bounding rectangles
-                // overlap, else the clipped-polygon (polyhedron) IoU, symmetric in its arguments
-                if (fminf(a.z, q.z) > fmaxf(a.x, q.x) && fminf(a.w, q.w) > fmaxf(a.y, q.y))
-                    s_queue[atomicAdd(&s_count, 1)] = (uint16_t)((t << 6) | j);
-                else if (zero_hits)
-                    bits |= 1ull << j;
+            S.bits[wd][t] = bits;
+            ++wd;
+            __syncthreads();
+            const int n1_now = S.n1;
+            __syncthreads();                                           // (the next word's pushes change n1)
+            const bool last = wd == MT_COLS / 64 || col0 + wd * 64 >= n;
+            if (!last && n1_now <= MC_Q1 - MT_ROWS * 64) continue;     // (uniform over the CTA)
+            filling = false;
+        }
+        // drain: first queue -> cheap test -> second queue -> exact test
+        const int n1 = S.n1;
+        int base = 0, n2 = 0;                                          // n2: entries of the second queue (uniform)
+#pragma unroll 1
+        while (true) {
+#pragma unroll 1
+            for (; base < n1 && n2 <= MC_Q2 - MT_ROWS; base += MT_ROWS) {
+                bool pass = false;
+                if (base + t < n1) {
+                    const int pr = S.q1[base + t], r = pr >> 8, c = pr & 255;
+                    pass = G::maybe(G::load(S.a0, S.a1, S.a2, c), G::load(S.r0, S.r1, S.r2, r), thr);
+                    if (pass) S.q2[atomicAdd(&S.n2, 1)] = (uint16_t)pr;
+                }
+                n2 += __syncthreads_count(pass);
             }
+            for (int k = t; k < n2; k += MT_ROWS) {
+                const int pr = S.q2[k], r = pr >> 8, c = pr & 255;
+                if (G::exact(G::load(S.a0, S.a1, S.a2, c), G::load(S.r0, S.r1, S.r2, r), thr))
+                    atomicOr(&S.bits[c >> 6][r], 1ull << (c & 63));
+            }
+            __syncthreads();
+            if (t == 0) S.n2 = 0;
+            n2 = 0;
+            __syncthreads();
+            if (base >= n1) break;
         }
-        s_bits[t] = bits;
+        if (t == 0) S.n1 = 0;
         __syncthreads();
-        const int cnt = s_count;
-        for (int k = t; k < cnt; k += MT_ROWS) {
-            const int pr = s_queue[k], r = pr >> 6, j = pr & 63;
-            if (G::exceeds(G::load(s_a0, s_a1, s_a2, wd * 64 + j), G::load(s_r0, s_r1, s_r2, r), thr))
-                atomicOr(&s_bits[r], 1ull << j);
-        }
-        __syncthreads();
-        if (t == 0) s_count = 0;
-        if (needed) {
-            const u64 out = s_bits[t];
+        if (wd == MT_COLS / 64 || col0 + wd * 64 >= n) break;
+        filling = true;
+    }
+    if (row_ok) {
+#pragma unroll 1
+        for (int w = 0; w < wd; ++w) {
+            const int c_start = col0 + w * 64;
+            if (c_start + 63 < i) continue;
+            const u64 out = S.bits[w][t];
             const int cw = c_start >> 6, kb = cw - (i >> 6);
             mask[(size_t)i * nw_stride + cw] = out;
             if (kb <= SW_L) band[((size_t)(i >> 6) * (SW_L + 1) + kb) * 64 + (i & 63)] = out;
         }
-        __syncthreads();
     }
 }
 
@@ -661,24 +704,28 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
     }
 }
 
-// The filter for the clipped pair tests, compacted like nms_mask_clip_kernel: per round of FC_CHUNK kept boxes every
-// thread pushes the (box, kept) pairs whose rectangles overlap onto a shared-memory queue, then all threads run the exact
-// tests with full warps.  The ordered compaction of the survivors is the same as in nms_filter_kernel.
+// The filter for the clipped pair tests, queued like nms_mask_clip_kernel: every thread pushes the (box, kept box)
+// pairs whose rectangles overlap onto a first shared-memory queue, FC_CHUNK kept boxes per round; when a further round
+// might not fit, and after the last one, all threads pop it, run the cheap test of the mode and push the undecided
+// pairs onto a second queue, which is evaluated exactly with full warps when it is nearly full and at the end.  The
+// ordered compaction of the survivors is the same as in nms_filter_kernel.
 constexpr int FC_CHUNK = 64;
+constexpr int FC_Q1 = 8192;        // entries of the first queue; a round adds at most FLT_BOXES x FC_CHUNK
+constexpr int FC_Q2 = 2048;
 
 template <int MODE>
-__global__ void __launch_bounds__(NMS_THREADS)
+__global__ void __launch_bounds__(NMS_THREADS, 2)
 nms_filter_clip_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__ order, int32_t *__restrict__ sc,
                        const int32_t *__restrict__ kept_rank, float thr, float4 *__restrict__ srect2,
                        uint32_t *__restrict__ order2, uint32_t *status, const Aux saux, const Aux saux2)
 {
     typedef PairGeom<MODE> G;
-    __shared__ float4 s_k[FC_CHUNK], s_k0[FC_CHUNK], s_k1[FC_CHUNK];
-    __shared__ float4 s_k2[MODE == PP_NMS_BOX3D ? FC_CHUNK : 1];
+    __shared__ float4 s_k[FC_CHUNK];
     __shared__ float4 s_b[FLT_BOXES], s_b0[FLT_BOXES], s_b1[FLT_BOXES];
     __shared__ float4 s_b2[MODE == PP_NMS_BOX3D ? FLT_BOXES : 1];
-    __shared__ uint16_t s_queue[FLT_BOXES * FC_CHUNK];
-    __shared__ int s_count;
+    __shared__ uint32_t s_q1[FC_Q1];                       // (box << 16) | index into the keep set
+    __shared__ uint32_t s_q2[FC_Q2];
+    __shared__ int s_n1, s_n2;
     __shared__ uint32_t s_tile, s_excl;
     __shared__ uint32_t s_warp[NMS_THREADS / 32];
     __shared__ unsigned char s_dead[FLT_BOXES];
@@ -686,7 +733,7 @@ nms_filter_clip_kernel(const float4 *__restrict__ srect, const uint32_t *__restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int num_tiles = (n - n1 + FLT_BOXES - 1) / FLT_BOXES;
     if ((int)blockIdx.x >= num_tiles) return;
-    if (tid == 0) { s_tile = atomicAdd((uint32_t *)&sc[SC_TICKET], 1u); s_count = 0; }
+    if (tid == 0) { s_tile = atomicAdd((uint32_t *)&sc[SC_TICKET], 1u); s_n1 = 0; s_n2 = 0; }
     if (tid < FLT_BOXES) s_dead[tid] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -704,37 +751,61 @@ nms_filter_clip_kernel(const float4 *__restrict__ srect, const uint32_t *__restr
     }
     const int bi = tid / FLT_SPLIT, part = tid % FLT_SPLIT;
     const bool zero_hits = 0.f > thr;
-    for (int k0 = 0; k0 < k1; k0 += FC_CHUNK) {
-        if (tid < FC_CHUNK && k0 + tid < k1) {
-            const int kr = kept_rank[k0 + tid];
-            s_k[tid] = srect[kr];
-            s_k0[tid] = saux.a0[kr];
-            s_k1[tid] = saux.a1[kr];
-            if (MODE == PP_NMS_BOX3D) s_k2[tid] = saux.a2[kr];
-        }
-        __syncthreads();
-        const int kn = min(FC_CHUNK, k1 - k0);
-        if (!s_dead[bi]) {
-            const float4 box = s_b[bi];
-            for (int j = part; j < kn; j += FLT_SPLIT) {
-                const float4 q = s_k[j];
-                // empty rectangle intersection -> iou == 0 exactly
-                if (fminf(box.z, q.z) > fmaxf(box.x, q.x) && fminf(box.w, q.w) > fmaxf(box.y, q.y))
-                    s_queue[atomicAdd(&s_count, 1)] = (uint16_t)((bi << 6) | j);
-                else if (zero_hits)
-                    s_dead[bi] = 1;
+    int k0 = 0;
+#pragma unroll 1
+    while (true) {
+        // fill: rounds of FC_CHUNK kept boxes until the next round might not fit
+#pragma unroll 1
+        for (; k0 < k1; k0 += FC_CHUNK) {
+            __syncthreads();                                   // s_k free, s_n1 settled
+            if (s_n1 > FC_Q1 - FLT_BOXES * FC_CHUNK) break;    // (uniform: the next push comes after the next barrier)
+            if (tid < FC_CHUNK && k0 + tid < k1) s_k[tid] = srect[kept_rank[k0 + tid]];
+            __syncthreads();
+            const int kn = min(FC_CHUNK, k1 - k0);
+            if (!s_dead[bi]) {
+                const float4 box = s_b[bi];
+                for (int j = part; j < kn; j += FLT_SPLIT) {
+                    const float4 q = s_k[j];
+                    // empty rectangle intersection -> iou == 0 exactly
+                    if (fminf(box.z, q.z) > fmaxf(box.x, q.x) && fminf(box.w, q.w) > fmaxf(box.y, q.y))
+                        s_q1[atomicAdd(&s_n1, 1)] = ((uint32_t)bi << 16) | (uint32_t)(k0 + j);
+                    else if (zero_hits)
+                        s_dead[bi] = 1;
+                }
             }
         }
         __syncthreads();
-        const int cnt = s_count;
-        for (int k = tid; k < cnt; k += NMS_THREADS) {
-            const int pr = s_queue[k], b = pr >> 6, j = pr & 63;
-            if (!s_dead[b] && G::exceeds(G::load(s_b0, s_b1, s_b2, b), G::load(s_k0, s_k1, s_k2, j), thr)) s_dead[b] = 1;
+        // drain
+        const int q1n = s_n1;
+        int base = 0, n2 = 0;
+#pragma unroll 1
+        while (true) {
+#pragma unroll 1
+            for (; base < q1n && n2 <= FC_Q2 - NMS_THREADS; base += NMS_THREADS) {
+                bool pass = false;
+                if (base + tid < q1n) {
+                    const uint32_t pr = s_q1[base + tid];
+                    const int b = pr >> 16, kr = kept_rank[pr & 0xFFFFu];
+                    pass = !s_dead[b] && G::maybe(G::load(s_b0, s_b1, s_b2, b), G::load(saux.a0, saux.a1, saux.a2, kr), thr);
+                    if (pass) s_q2[atomicAdd(&s_n2, 1)] = pr;
+                }
+                n2 += __syncthreads_count(pass);
+            }
+            for (int k = tid; k < n2; k += NMS_THREADS) {
+                const uint32_t pr = s_q2[k];
+                const int b = pr >> 16, kr = kept_rank[pr & 0xFFFFu];
+                if (!s_dead[b] && G::exact(G::load(s_b0, s_b1, s_b2, b), G::load(saux.a0, saux.a1, saux.a2, kr), thr)) s_dead[b] = 1;
+            }
+            __syncthreads();
+            if (tid == 0) s_n2 = 0;
+            n2 = 0;
+            __syncthreads();
+            if (base >= q1n) break;
         }
+        if (tid == 0) s_n1 = 0;
         __syncthreads();
-        if (tid == 0) s_count = 0;
+        if (k0 >= k1) break;
     }
-    __syncthreads();
     // ordered compaction: block scan of the survivor flags + decoupled look-back over the (ticket-ordered) tiles
     const bool alive = tid < FLT_BOXES && !s_dead[tid];
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
@@ -836,7 +907,12 @@ int launch_level(const float4 *rects, const int32_t *n_ptr, int64_t n_max, float
     dim3 grid((unsigned)ceil_div(n_max, MT_COLS), (unsigned)ceil_div(n_max, MT_ROWS));
     // thr >= 0: a pair whose bounding rectangles are apart has iou == 0, which only exceeds a negative threshold
 #define PP_MASK(PF, MD) nms_mask_kernel<PF, MD><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, saux)
-#define PP_MASKC(PF, MD) nms_mask_clip_kernel<PF, MD><<<grid, MT_ROWS, 0, st>>>(rects, n_ptr, thr, nw, mask, band, saux)
+#define PP_MASKC(PF, MD)                                                                                              \
+    do {                                                                                                              \
+        cudaFuncSetAttribute(nms_mask_clip_kernel<PF, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                             (int)sizeof(ClipSmem<MD>));                                                              \
+        nms_mask_clip_kernel<PF, MD><<<grid, MT_ROWS, sizeof(ClipSmem<MD>), st>>>(rects, n_ptr, thr, nw, mask, band, saux); \
+    } while (0)
     if (mode == PP_NMS_BOX3D) { if (thr >= 0.f) PP_MASKC(true, PP_NMS_BOX3D); else PP_MASKC(false, PP_NMS_BOX3D); }
     else if (mode == PP_NMS_ROT_BEV) { if (thr >= 0.f) PP_MASKC(true, PP_NMS_ROT_BEV); else PP_MASKC(false, PP_NMS_ROT_BEV); }
     else { if (thr >= 0.f) PP_MASK(true, PP_NMS_AABB2D); else PP_MASK(false, PP_NMS_AABB2D); }
