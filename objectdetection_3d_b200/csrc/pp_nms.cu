@@ -119,9 +119,18 @@ nms_gather_kernel(const float4 *__restrict__ rect, const uint32_t *__restrict__ 
     }
 }
 
-constexpr int SW_L = 7;                     // words after the diagonal handled by the sweep's resolver warp
-constexpr int SW_RING = 8;                  // band blocks in flight in the sweep
-constexpr int SW_BAND = (SW_L + 1) * 64;    // u64 per band block: band[b][k][row] = mask[64b + row][b + k]
+constexpr int SW_L = 31;                    // words after the diagonal handled by the sweep's resolver warp (one per lane)
+constexpr int SW_RING = 6;                  // band blocks in flight in the sweep
+constexpr int SW_BAND = (SW_L + 1) * 64;    // u64 per band block (64 rows x the diagonal word and the SW_L words after it)
+// Layout of one band block: the 64 diagonal words first (the resolver's lanes read rows l and l + 32 of them), then the
+// rows' next SW_L words row by row (a kept row's words are read by consecutive lanes: no bank conflicts).
+__device__ __forceinline__ size_t band_index(int row, int kb)
+{
+    const size_t blk = (size_t)(row >> 6) * SW_BAND;
+    const int r = row & 63;
+    return kb == 0 ? blk + r : blk + 64 + (size_t)r * SW_L + (kb - 1);
+}
+constexpr size_t SW_SMEM_MAX = 200 * 1024;  // dynamic shared memory the sweep may ask for
 
 constexpr int MT_ROWS = 128;   // rows (selected boxes) per CTA, one per thread
 constexpr int MT_COLS = 256;   // columns (remaining boxes) per CTA = 4 mask words
@@ -228,8 +237,8 @@ nms_mask_kernel(const float4 *__restrict__ srect, const int32_t *__restrict__ n_
         }
         const int cw = c_start >> 6, kb = cw - (i >> 6);
         mask[(size_t)i * nw_stride + cw] = bits;
-        // tile-major copy of the diagonal band, streamed by the sweep with one bulk copy per block
-        if (kb <= SW_L) band[((size_t)(i >> 6) * (SW_L + 1) + kb) * 64 + (i & 63)] = bits;
+        // block-major copy of the diagonal band, streamed by the sweep with one bulk copy per block
+        if (kb <= SW_L) band[band_index(i, kb)] = bits;
     }
 }
 
@@ -385,21 +394,31 @@ nms_mask_clip_kernel(const float4 *__restrict__ srect, const int32_t *__restrict
             const u64 out = S.bits[w][t];
             const int cw = c_start >> 6, kb = cw - (i >> 6);
             mask[(size_t)i * nw_stride + cw] = out;
-            if (kb <= SW_L) band[((size_t)(i >> 6) * (SW_L + 1) + kb) * 64 + (i & 63)] = out;
+            if (kb <= SW_L) band[band_index(i, kb)] = out;
         }
     }
 }
 
 // ---- sweep -------------------------------------------------------------------------------------
-// One CTA.  Warp 31 ("resolver") walks the 64-box blocks in rank order: it takes the final removed word of
-// block b, keeps the surviving boxes with a find-first-set chain over the diagonal word (one iteration per
-// KEPT box) and ORs the kept rows' next SW_L words itself, from a band of the mask that it streams into a
-// shared-memory ring with cp.async SW_RING blocks ahead.  The other 31 warps ("owners") each own mask words
-// w and accumulate the kept rows of all blocks <= w - SW_L - 1 as those blocks get resolved, so their L2
-// latency is hidden behind SW_L resolver steps.  Synchronisation is through shared-memory counters only.
+// One CTA.  Warp 31 ("resolver") walks the 64-box blocks in rank order.  Per block it takes the final removed word,
+// decides the block's keep set with the whole warp -- lane l holds rows l and l + 32 of the 64 x 64 diagonal tile; per
+// round the candidates that no other candidate suppresses are kept and what they suppress leaves the candidate set
+// (two OR-reductions over the warp per round, as many rounds as the longest suppression chain inside the block, not
+// one step per kept box) -- and ORs the kept rows into the next SW_L words itself, again as warp OR-reductions, from a
+// band of the mask that it streams into a shared-memory ring with bulk copies SW_RING - 1 blocks ahead.  The other 31
+// warps ("owners") take the resolved blocks round-robin and OR their kept rows into all words beyond the band, lanes
+// over consecutive words (coalesced 256-byte reads of the mask, 8 rows in flight); the resolver needs block b - SW_L - 1
+// finished when it reaches block b, so the owners' L2 latency hides behind SW_L resolver steps.  Synchronisation is
+// through shared-memory flags only.
 
 // acquire/release fence at CTA scope (MEMBAR.ALL.CTA): cheaper than __threadfence_block()'s fence.sc
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ u64 warp_or64(u64 v)
+{
+    const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)v), hi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(v >> 32));
+    return ((u64)hi << 32) | lo;
+}
+constexpr int SW_OWN_ROWS = 8;              // mask rows an owner lane has in flight (64 registers per thread at 1024 threads)
 
 __global__ void __launch_bounds__(SWEEP_THREADS)
 nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int nw_stride,
@@ -409,10 +428,10 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
 {
     extern __shared__ __align__(16) u64 sw_smem[];
     u64 *ring = sw_smem;                                   // [SW_RING][SW_L+1][64]
-    u64 *removed = ring + SW_RING * SW_BAND;               // [nw_cap]
+    u64 *removed = ring + SW_RING * SW_BAND;               // [nw_cap] owners' contributions (atomics)
     u64 *kept_arr = removed + nw_cap;                      // [nw_cap]
     u64 *removed_r = kept_arr + nw_cap;                    // [nw_cap] resolver-side contributions (no atomics)
-    volatile int *ready = (volatile int *)(removed_r + nw_cap);  // [nw_cap]
+    volatile int *done = (volatile int *)(removed_r + nw_cap);   // [nw_cap] block b's rows are in every word beyond its band
     __shared__ volatile int s_resolved;
     __shared__ __align__(8) u64 s_mbar[SW_RING];
     const int n = *n_cand;
@@ -420,8 +439,9 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef PP_TIMING
     long long t_start = clock64(), t_loop0 = 0, t_loop1 = 0, t_wait = 0, t_chain = 0;
+    int rounds = 0;
 #endif
-    for (int w = tid; w < nw; w += SWEEP_THREADS) { removed[w] = 0; removed_r[w] = 0; ready[w] = 0; }
+    for (int w = tid; w < nw; w += SWEEP_THREADS) { removed[w] = 0; removed_r[w] = 0; done[w] = 0; }
     if (tid == 0) {
         s_resolved = 0;
         for (int r = 0; r < SW_RING; ++r)
@@ -433,7 +453,7 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
 
     if (warp == SWEEP_THREADS / 32 - 1) {
         // ------------------------------------------------------------------ resolver
-        // band of block b (4 KB, contiguous) -> ring slot b % SW_RING with one TMA bulk copy, SW_RING-1 ahead
+        // band of block b (16 KB, contiguous) -> ring slot b % SW_RING with one TMA bulk copy, SW_RING-1 ahead
         auto issue_band = [&](int b) {
             if (b < nw && lane == 0) {
                 const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar[b % SW_RING]);
@@ -463,113 +483,113 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
             }
             const u64 *slot = ring + (b % SW_RING) * SW_BAND;
             if (b > SW_L) {
-                while (ready[b] == 0) { }      // pure spin: __nanosleep granularity (~1 us) would dominate the step
+                while (done[b - SW_L - 1] == 0) { }      // pure spin: __nanosleep granularity (~1 us) would dominate the step
+                fence_cta();
             }
-            fence_cta();
 #ifdef PP_TIMING
             const long long tw1 = clock64();
             t_wait += tw1 - tw0;
 #endif
             const int valid = min(64, n - b * 64);
-            u64 alive = ~(*(volatile u64 *)(removed + b) | *(volatile u64 *)(removed_r + b));
-            if (valid < 64) alive &= (1ull << valid) - 1;
-            // the chain over the KEPT boxes of the block, on 32-bit halves (one find-first-set + one shared-memory read
-            // per kept box on the dependent path)
-            uint32_t alo = (uint32_t)alive, ahi = (uint32_t)(alive >> 32), klo = 0u, khi = 0u;
-            while (alo) {
-                const int i = __ffs((int)alo) - 1;
-                const u64 row = slot[i];
-                klo |= 1u << i;
-                alo &= ~((uint32_t)row | (1u << i));
-                ahi &= ~(uint32_t)(row >> 32);
+            u64 cand = ~(*(volatile u64 *)(removed + b) | *(volatile u64 *)(removed_r + b));
+            if (valid < 64) cand &= (1ull << valid) - 1;
+            // rows lane and lane + 32 of the diagonal tile (bit j of row i is set only for j > i); rows that are not
+            // boxes hold whatever the workspace held, and are never candidates
+            const u64 d0 = slot[lane], d1 = slot[32 + lane];
+            u64 kept = 0;
+            while (cand) {
+                const u64 mine = (((cand >> lane) & 1ull) ? d0 : 0ull) | (((cand >> (32 + lane)) & 1ull) ? d1 : 0ull);
+                const u64 nk = cand & ~warp_or64(mine);           // candidates no candidate suppresses: kept
+                kept |= nk;
+                const u64 theirs = (((nk >> lane) & 1ull) ? d0 : 0ull) | (((nk >> (32 + lane)) & 1ull) ? d1 : 0ull);
+                cand &= ~(nk | warp_or64(theirs));
+#ifdef PP_TIMING
+                ++rounds;
+#endif
             }
-            while (ahi) {
-                const int i = __ffs((int)ahi) - 1;
-                khi |= 1u << i;
-                ahi &= ~((uint32_t)(slot[32 + i] >> 32) | (1u << i));
-            }
-            const u64 kept = ((u64)khi << 32) | klo;
 #ifdef PP_TIMING
             t_chain += clock64() - tw1;
 #endif
             if (lane == 0) {
                 kept_arr[b] = kept;
-                fence_cta();
-                s_resolved = b + 1;
-            }
-            // lanes 1..SW_L each own one of the next words: OR the kept rows' band words (shared memory)
-            if (kept && lane >= 1 && lane <= SW_L && b + lane < nw) {
-                u64 v = 0, k = kept;
-                while (k) {
-                    const int i = __ffsll((long long)k) - 1;
-                    k &= k - 1;
-                    v |= slot[lane * 64 + i];
+                if (nw > SW_L + 1) {           // (no owners otherwise: the band holds every word)
+                    fence_cta();
+                    s_resolved = b + 1;
                 }
-                if (v) *(volatile u64 *)(removed_r + b + lane) |= v;   // one lane per word per step
+            }
+            // the kept rows' next SW_L words: lane k ORs word b + k of every kept row.  All 64 rows are read (consecutive
+            // lanes read consecutive words of a row: no bank conflicts) and masked by their kept bit: 64 independent
+            // loads the compiler batches, instead of one dependent find-first-set + load per kept box.
+            if (kept) {
+                const u64 *rows = slot + 64 + (lane > 0 ? lane - 1 : 0);
+                const uint32_t klo = (uint32_t)kept, khi = (uint32_t)(kept >> 32);
+                uint32_t vlo = 0, vhi = 0;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const u64 t = rows[i * SW_L];
+                    if ((i < 32 ? klo >> i : khi >> (i - 32)) & 1u) { vlo |= (uint32_t)t; vhi |= (uint32_t)(t >> 32); }
+                }
+                const u64 v = ((u64)vhi << 32) | vlo;
+                if (v && lane > 0 && b + lane < nw) *(volatile u64 *)(removed_r + b + lane) |= v;   // one lane per word per step
             }
             __syncwarp();      // orders the lanes' shared-memory traffic; the slot may be refilled next step
         }
 #ifdef PP_TIMING
         t_loop1 = clock64();
         if (lane == 0)
-            printf("sweep n=%d blocks=%d: init %lld | loop %lld cycles = %lld per block (wait %lld, chain %lld)\n", n, nw,
+            printf("sweep n=%d blocks=%d: init %lld | loop %lld cycles = %lld per block (wait %lld, rounds %lld, %d rounds)\n", n, nw,
                    t_loop0 - t_start, t_loop1 - t_loop0, (t_loop1 - t_loop0) / (nw > 0 ? nw : 1), t_wait / (nw > 0 ? nw : 1),
-                   t_chain / (nw > 0 ? nw : 1));
+                   t_chain / (nw > 0 ? nw : 1), rounds);
 #endif
     } else {
         // ------------------------------------------------------------------ owners
-        const int n_owner = SWEEP_THREADS - 32;
-        for (int w = tid; w < nw; w += n_owner) {
-            const int last = w - SW_L - 1;      // blocks 0..last reach word w through this thread
-            u64 acc = 0, k = 0;
-            int b = 0, hi = -1;
-            bool have = false;                  // k holds the not yet consumed kept bits of block b
-            while (true) {
-                if (!have) {
-                    if (b > last) break;
-                    const int res = s_resolved;
-                    if (res <= b) continue;
-                    fence_cta();
-                    hi = min(res - 1, last);
-                    k = *(volatile u64 *)(kept_arr + b);
-                    have = true;
-                }
-                // gather up to 8 kept rows of the resolved blocks, then issue their loads back to back: an
-                // in-order warp stalls at the first use, so loads ORed one by one would serialise the L2 latency
-                long long off[8];
+        const int n_owner = SWEEP_THREADS / 32 - 1;
+        for (int b = warp; b + SW_L + 1 < nw; b += n_owner) {
+            while (s_resolved <= b) __nanosleep(100);
+            fence_cta();
+            u64 k = *(volatile u64 *)(kept_arr + b);
+            const int w0 = b + SW_L + 1;
+            // rows of this block, SW_OWN_ROWS at a time; per group every lane ORs its words and issues one atomic each
+            while (k) {
+                int row[SW_OWN_ROWS];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    while (k == 0 && b < hi) { ++b; k = *(volatile u64 *)(kept_arr + b); }
-                    off[j] = -1;
+                for (int j = 0; j < SW_OWN_ROWS; ++j) {
+                    row[j] = -1;
                     if (k) {
                         const int i = __ffsll((long long)k) - 1;
                         k &= k - 1;
-                        off[j] = (long long)(b * 64 + i) * nw_stride + w;
+                        row[j] = b * 64 + i;
                     }
                 }
-                u64 v[8];
+                for (int w = w0 + lane; w < nw; w += 32) {
+                    u64 v[SW_OWN_ROWS];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? mask[off[j]] : 0ull;
+                    for (int j = 0; j < SW_OWN_ROWS; ++j) v[j] = row[j] >= 0 ? mask[(size_t)row[j] * nw_stride + w] : 0ull;
+                    u64 acc = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc |= v[j];
-                if (k == 0 && b >= hi) { have = false; b = hi + 1; }
+                    for (int j = 0; j < SW_OWN_ROWS; ++j) acc |= v[j];
+                    if (acc) atomicOr(removed + w, acc);
+                }
             }
-            if (acc) atomicOr(removed + w, acc);
-            fence_cta();
-            ready[w] = 1;
+            __syncwarp();
+            if (lane == 0) {
+                fence_cta();
+                done[b] = 1;
+            }
         }
     }
     // ---- expand the kept bitmaps to original indices, in rank order (all threads) -------------------
+    // exclusive prefix of the words' kept counts (block scan per 1024 words), then one thread per box
     __syncthreads();
     __shared__ int s_warp_sum[SWEEP_THREADS / 32];
     __shared__ int s_base;
+    int *prefix = reinterpret_cast<int *>(removed);    // (the removed words are no longer needed)
     const int base0 = keep_base ? *keep_base : 0;      // keep entries of the previous level come first
     if (tid == 0) s_base = base0;
     __syncthreads();
     for (int w0 = 0; w0 < nw; w0 += SWEEP_THREADS) {
         const int w = w0 + tid;
-        const u64 kept = w < nw ? kept_arr[w] : 0ull;
-        const int cnt = __popcll(kept);
+        const int cnt = w < nw ? __popcll(kept_arr[w]) : 0;
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -580,16 +600,18 @@ nms_sweep_kernel(const u64 *__restrict__ mask, const u64 *__restrict__ band, int
         __syncthreads();
         int pos = s_base + incl - cnt;
         for (int q = 0; q < warp; ++q) pos += s_warp_sum[q];
-        u64 k = kept;
-        while (k) {
-            const int i = __ffsll((long long)k) - 1;
-            k &= k - 1;
-            if (kept_rank) kept_rank[pos - base0] = w * 64 + i;
-            keep[pos++] = (int64_t)order[w * 64 + i];
+        if (w < nw) prefix[w] = pos;
+        __syncthreads();
+        if (tid == SWEEP_THREADS - 1) s_base = pos + cnt;      // last thread holds the running total
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += SWEEP_THREADS) {
+        const u64 kept = kept_arr[i >> 6];
+        if ((kept >> (i & 63)) & 1ull) {
+            const int pos = prefix[i >> 6] + __popcll(kept & ((1ull << (i & 63)) - 1ull));
+            if (kept_rank) kept_rank[pos - base0] = i;
+            keep[pos] = (int64_t)order[i];
         }
-        __syncthreads();
-        if (tid == SWEEP_THREADS - 1) s_base = pos;      // last thread holds the running total
-        __syncthreads();
     }
     if (tid == 0) {
         *keep_count = s_base;
@@ -875,9 +897,11 @@ NmsWs carve(void *ws, int64_t N, int mode, size_t *total)
     Arena a(ws, (size_t)-1);
     w.sc = a.take<int32_t>(64);
     w.status = a.take<uint32_t>((size_t)ceil_div(l2 > 0 ? l2 : 1, FLT_BOXES));
+    w.zero_bytes = a.off;
+    // (the bands need no zeroing: every word the sweep reads of a box's rows is written by the mask kernel, and rows
+    // that are not boxes are never candidates)
     w.band1 = a.take<u64>((size_t)w.nw1 * SW_BAND);
     w.band2 = a.take<u64>(l2 > 0 ? (size_t)w.nw2 * SW_BAND : 1);
-    w.zero_bytes = a.off;
     w.rect = a.take<float4>((size_t)n1);
     w.srect = a.take<float4>((size_t)n1);
     w.srect2 = a.take<float4>((size_t)(l2 > 0 ? l2 : 1));
@@ -920,7 +944,7 @@ int launch_level(const float4 *rects, const int32_t *n_ptr, int64_t n_max, float
 #undef PP_MASKC
     if (int rc = check_launch("nms_mask_kernel")) return rc;
     const size_t smem = ((size_t)SW_RING * SW_BAND + 3 * (size_t)nw) * sizeof(u64) + (size_t)nw * sizeof(int);
-    PP_REQUIRE(smem <= 96 * 1024, "too many boxes for the sweep's shared memory");
+    PP_REQUIRE(smem <= SW_SMEM_MAX, "too many boxes for the sweep's shared memory");
     nms_sweep_kernel<<<1, SWEEP_THREADS, smem, st>>>(mask, band, nw, n_ptr, order, keep, keep_base, keep_count, kept_rank,
                                                      kept_n, nw);
     return check_launch("nms_sweep_kernel");
@@ -961,10 +985,10 @@ extern "C" int pp_nms_mode(const float *boxes9, const float *scores, int64_t sco
         set_error("nms workspace too small: %zu < %zu", workspace_bytes, total);
         return PP_ERR_WORKSPACE;
     }
-    PP_CUDA_TRY(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));     // scalars, look-back state, diagonal bands
+    PP_CUDA_TRY(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));     // scalars, look-back state
     prof_mark("memset");
     // per device and context, cheap: set on every call (a process may drive several GPUs, from several threads)
-    PP_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    PP_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_MAX));
     const unsigned nb = (unsigned)ceil_div(N, NMS_THREADS);
     nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.sc + SC_N,
                                                    iou_mode, w.aux);
