@@ -1,5 +1,6 @@
 // Shared helpers for libpp_b200 (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -81,6 +82,24 @@ __device__ __forceinline__ void pdl_enter()
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The same, for kernels that read what the predecessor wrote through `const T *__restrict__` parameters: such loads are
+// ld.global.nc, which the compiler may move ABOVE the wait (observed on the NMS kernels, whose first load -- the
+// candidate count -- was hoisted over both instructions: the "memory" clobber does not order loads of data the
+// compiler is told nobody writes; scripts/pdl_audit.py lists what precedes the wait in the built objects).  Passing the pointers
+// through an empty asm after the wait makes every load through them depend on it.
+template <typename P> __device__ __forceinline__ void pdl_launder(P &p) { asm volatile("" : "+l"(p)); }
+template <typename... P> __device__ __forceinline__ void pdl_enter(P &...ptrs)
+{
+    pdl_enter();
+    (pdl_launder(ptrs), ...);
+}
+
+// development switch: PP_NO_PDL=1 in the environment launches everything the plain way
+inline bool pdl_allowed()
+{
+    static const bool on = [] { const char *e = getenv("PP_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -95,7 +114,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_allowed() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -897,7 +897,10 @@ NmsWs carve(void *ws, int64_t N, int mode, size_t *total)
     Arena a(ws, (size_t)-1);
     w.sc = a.take<int32_t>(64);
     w.status = a.take<uint32_t>((size_t)ceil_div(l2 > 0 ? l2 : 1, FLT_BOXES));
-    w.zero_bytes = a.off;
+    // the sort's counters are zeroed together with ours (one memset per call)
+    w.sort_ws_bytes = sort_workspace_bytes(n1);
+    w.sort_ws = a.take<char>(w.sort_ws_bytes);
+    w.zero_bytes = (size_t)((char *)w.sort_ws - (char *)ws) + sort_zero_bytes(n1);
     // (the bands need no zeroing: every word the sweep reads of a box's rows is written by the mask kernel, and rows
     // that are not boxes are never candidates)
     w.band1 = a.take<u64>((size_t)w.nw1 * SW_BAND);
@@ -918,8 +921,6 @@ NmsWs carve(void *ws, int64_t N, int mode, size_t *total)
             *slots[g][k] = k < naux ? a.take<float4>((size_t)(g == 2 ? (l2 > 0 ? l2 : 1) : n1)) : nullptr;
     w.mask1 = a.take<u64>((size_t)l1 * w.nw1);
     w.mask2 = a.take<u64>(l2 > 0 ? (size_t)l2 * w.nw2 : 1);
-    w.sort_ws_bytes = sort_workspace_bytes(n1);
-    w.sort_ws = a.take<char>(w.sort_ws_bytes);
     *total = align_up(a.off);
     return w;
 }
@@ -985,7 +986,7 @@ extern "C" int pp_nms_mode(const float *boxes9, const float *scores, int64_t sco
         set_error("nms workspace too small: %zu < %zu", workspace_bytes, total);
         return PP_ERR_WORKSPACE;
     }
-    PP_CUDA_TRY(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));     // scalars, look-back state
+    PP_CUDA_TRY(cudaMemsetAsync(workspace, 0, w.zero_bytes, st));     // scalars, look-back state, the sort's counters
     prof_mark("memset");
     // per device and context, cheap: set on every call (a process may drive several GPUs, from several threads)
     PP_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_MAX));
@@ -993,7 +994,7 @@ extern "C" int pp_nms_mode(const float *boxes9, const float *scores, int64_t sco
     nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.sc + SC_N,
                                                    iou_mode, w.aux);
     if (int rc = check_launch("nms_prepare_kernel")) return rc;
-    if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st)) return rc;
+    if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st, true)) return rc;
     nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.sc, w.srect, NMS_LEVEL1, w.aux, w.saux);
     if (int rc = check_launch("nms_gather_kernel")) return rc;
     // level 1: greedy NMS of the NMS_LEVEL1 best-scored candidates

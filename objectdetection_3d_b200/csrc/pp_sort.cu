@@ -286,8 +286,14 @@ size_t sort_workspace_bytes(int64_t n)
     return total;
 }
 
+size_t sort_zero_bytes(int64_t n)
+{
+    size_t total;
+    return carve(nullptr, n, &total).zero_bytes;
+}
+
 int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
-                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st)
+                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st, bool ws_zeroed)
 {
     if (n <= 0) return PP_OK;
     PP_REQUIRE(n < (1ll << 30), "n must be < 2^30");
@@ -303,8 +309,10 @@ int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *k
         sort_small_kernel<<<1, SMALL_THREADS, SMALL_SMEM, st>>>(keys_in, vals_in, keys_out, vals_out, (int)n);
         return check_launch("sort_small_kernel");
     }
-    PP_CUDA_TRY(cudaMemsetAsync(ws, 0, s.zero_bytes, st));
-    prof_mark("memset");
+    if (!ws_zeroed) {
+        PP_CUDA_TRY(cudaMemsetAsync(ws, 0, s.zero_bytes, st));
+        prof_mark("memset");
+    }
     int hist_blocks = (int)(ceil_div(n, SORT_THREADS * 16) < 148 * 4 ? ceil_div(n, SORT_THREADS * 16) : 148 * 4);
     sort_hist_kernel<<<hist_blocks, SORT_THREADS, 0, st>>>(keys_in, n, s.hist);
     if (int rc = check_launch("sort_hist_kernel")) return rc;
