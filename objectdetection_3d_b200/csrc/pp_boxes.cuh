@@ -127,59 +127,7 @@ __device__ __forceinline__ float4 rrect_aabb(const RRect &r)
     return make_float4(r.cx - ex, r.cy - ey, r.cx + ex, r.cy + ey);
 }
 
-// Area of the intersection of two rotated rectangles: Sutherland-Hodgman clipping of a's corners against the four
-// half-planes of b, evaluated in b's frame (where b is axis-aligned), then the shoelace formula.  FP32 CUDA cores.
-__device__ __forceinline__ float rrect_inter_area(const RRect &a, const RRect &b)
-{
-    float px[8], py[8], qx[8], qy[8];
-    const float sx[4] = {-1.f, 1.f, 1.f, -1.f}, sy[4] = {-1.f, -1.f, 1.f, 1.f};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float wx = a.cx + a.c * sx[i] * a.hx - a.s * sy[i] * a.hy - b.cx;
-        const float wy = a.cy + a.s * sx[i] * a.hx + a.c * sy[i] * a.hy - b.cy;
-        px[i] = b.c * wx + b.s * wy;
-        py[i] = -b.s * wx + b.c * wy;
-    }
-    int n = 4;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const bool yaxis = e >= 2;
-        const float sgn = (e & 1) ? -1.f : 1.f, lim = yaxis ? b.hy : b.hx;
-        int m = 0;
-        for (int i = 0; i < n; ++i) {
-            const int j = (i + 1 == n) ? 0 : i + 1;
-            const float ci = sgn * (yaxis ? py[i] : px[i]) - lim, cj = sgn * (yaxis ? py[j] : px[j]) - lim;
-            if (ci <= 0.f) { qx[m] = px[i]; qy[m] = py[i]; ++m; }
-            if ((ci < 0.f && cj > 0.f) || (ci > 0.f && cj < 0.f)) {
-                const float t = ci / (ci - cj);
-                qx[m] = px[i] + t * (px[j] - px[i]);
-                qy[m] = py[i] + t * (py[j] - py[i]);
-                ++m;
-            }
-        }
-        n = m;
-        for (int i = 0; i < n; ++i) { px[i] = qx[i]; py[i] = qy[i]; }
-    }
-    float area = 0.f;
-    for (int i = 0; i < n; ++i) {
-        const int j = (i + 1 == n) ? 0 : i + 1;
-        area += px[i] * py[j] - px[j] * py[i];
-    }
-    return 0.5f * fabsf(area);
-}
-
-// Symmetric by construction: the pair is put into a canonical order before clipping, so iou(a,b) == iou(b,a)
-// bit for bit (the NMS decision must not depend on which box is "selected" and which "remaining").
-__device__ __forceinline__ float rrect_iou(const RRect &a, const RRect &b)
-{
-    const bool swap = (a.cx > b.cx) || (a.cx == b.cx && (a.cy > b.cy || (a.cy == b.cy && (a.hx > b.hx ||
-                      (a.hx == b.hx && (a.hy > b.hy || (a.hy == b.hy && a.s > b.s)))))));
-    const float inter = swap ? rrect_inter_area(b, a) : rrect_inter_area(a, b);
-    const float aa = 4.f * a.hx * a.hy, ab = 4.f * b.hx * b.hy;
-    const float uni = (swap ? ab + aa : aa + ab) - inter;
-    return inter / fmaxf(uni, 1e-6f);
-}
-
+// (intersection area and IoU of two footprints: rrect_inter_area / rrect_iou at the end of this file)
 // RRect <-> (float4, float2) for 16/8-byte loads and stores
 __device__ __forceinline__ float4 rrect_lo(const RRect &r) { return make_float4(r.cx, r.cy, r.hx, r.hy); }
 __device__ __forceinline__ float2 rrect_hi(const RRect &r) { return make_float2(r.c, r.s); }
@@ -197,6 +145,13 @@ struct Box3 {
 };
 #ifndef PP_B3_FN
 #define PP_B3_FN __device__ __forceinline__
+// The two IoU entry points are NOT inlined: every kernel of a translation unit then runs the same instructions, so the
+// IoU matrix kernels, the assignment kernel and the NMS kernels agree bit for bit (inlined copies may contract
+// multiply-adds differently).
+#define PP_B3_ENTRY static __device__ __noinline__
+#endif
+#ifndef PP_B3_ENTRY
+#define PP_B3_ENTRY PP_B3_FN
 #endif
 
 __device__ __forceinline__ Box3 box3_from_corners(const float *c /* (8,3) */)
@@ -327,12 +282,12 @@ PP_B3_FN void b3_lines(B3Lines &L)
     }
 }
 // area of { (u, v) in [0,1]^2 : lo <= c0[k] + cu[k] u + cv[k] v <= hi, k = 0..2 }
-PP_B3_FN double b3_area(const B3Lines &L, const double c0[3], double lo, double hi)
+PP_B3_FN double b3_area(const B3Lines &L, const double c0[3], const double lo[3], const double hi[3])
 {
     // edge u = 1, parameter v
     double tmin = 0.0, tmax = 1.0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) b3_cut(tmin, tmax, c0[k] + L.cu[k], L.rcv[k], L.rcv[k] >= 0.0, lo, hi);
+    for (int k = 0; k < 3; ++k) b3_cut(tmin, tmax, c0[k] + L.cu[k], L.rcv[k], L.rcv[k] >= 0.0, lo[k], hi[k]);
     double area = tmax > tmin ? tmax - tmin : 0.0;
     // strip lines: P + t D with D = (cv, -cu); the interior is on the left of D for the lo line, on the right for hi
 #pragma unroll
@@ -345,13 +300,13 @@ PP_B3_FN double b3_area(const B3Lines &L, const double c0[3], double lo, double 
         const bool p_u = r_u >= 0.0, p_v = r_v >= 0.0, p_j = r_j >= 0.0, p_m = r_m >= 0.0;
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
-            const double sc = ((side ? hi : lo) - c0[k]) * L.rnn[k];
+            const double sc = ((side ? hi[k] : lo[k]) - c0[k]) * L.rnn[k];
             const double pu = L.cu[k] * sc, pv = L.cv[k] * sc;
             double t0 = -1e300, t1 = 1e300;
             b3_cut(t0, t1, pu, r_u, p_u, 0.0, 1.0);
             b3_cut(t0, t1, pv, r_v, p_v, 0.0, 1.0);
-            b3_cut(t0, t1, c0[j] + L.cu[j] * pu + L.cv[j] * pv, r_j, p_j, lo, hi);
-            b3_cut(t0, t1, c0[m] + L.cu[m] * pu + L.cv[m] * pv, r_m, p_m, lo, hi);
+            b3_cut(t0, t1, c0[j] + L.cu[j] * pu + L.cv[j] * pv, r_j, p_j, lo[j], hi[j]);
+            b3_cut(t0, t1, c0[m] + L.cu[m] * pu + L.cv[m] * pv, r_m, p_m, lo[m], hi[m]);
             const double c = 0.5 * (2.0 * pu + (t0 + t1) * du) * ((t1 - t0) * dv);
             const bool ok = t1 > t0 && L.rnn[k] != 0.0;
             area += ok ? (side ? -c : c) : 0.0;
@@ -417,6 +372,24 @@ PP_B3_FN double box3_inter_volume(const Box3 &a, const Box3 &b, double &va, doub
         for (int c = 0; c < 3; ++c) mat[1][c][k] = gp[k][c];
     }
     const double sg = dp < 0.0 ? -1.0 : 1.0;
+    // The widening of the closed strips (b's frame) and the narrowing of the open ones (a's frame) are the SAME length
+    // in space, B3_EPS times the longest edge of the pair, expressed in each axis' own unit: two nearly coplanar faces
+    // -- coplanar up to the fp32 rounding of the corners, i.e. tilted against each other by 1e-8 -- are then told
+    // apart by the same distance from both sides, and every point of their common plane is counted exactly once.
+    double len2 = 0.0, la[3], lb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        la[k] = ae[k][0] * ae[k][0] + ae[k][1] * ae[k][1] + ae[k][2] * ae[k][2];
+        lb[k] = be[k][0] * be[k][0] + be[k][1] * be[k][1] + be[k][2] * be[k][2];
+        len2 = fmax(len2, fmax(la[k], lb[k]));
+    }
+    double lo[2][3], hi[2][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double eb = B3_EPS * sqrt(len2 / lb[k]), ea = B3_EPS * sqrt(len2 / la[k]);
+        lo[0][k] = -0.5 - eb; hi[0][k] = 0.5 + eb;
+        lo[1][k] = ea;        hi[1][k] = 1.0 - ea;
+    }
     double sum = 0.0;
 #pragma unroll 1
     for (int task = 0; task < 6; ++task) {
@@ -432,8 +405,7 @@ PP_B3_FN double box3_inter_volume(const Box3 &a, const Box3 &b, double &va, doub
             L.cv[k] = mat[which][ib][k];
         }
         b3_lines(L);
-        const double lo = which ? B3_EPS : -0.5 - B3_EPS, hi = which ? 1.0 - B3_EPS : 0.5 + B3_EPS;
-        const double a0 = b3_area(L, c0a, lo, hi), a1 = b3_area(L, c0b, lo, hi);
+        const double a0 = b3_area(L, c0a, lo[which], hi[which]), a1 = b3_area(L, c0b, lo[which], hi[which]);
         // cone weights: a's faces sigma * det(O, E1, E2) = -h0 (low side), h0 + dp (high side), times sign(dp);
         // the cube's faces are at distance 1/2 from the apex
         const double h0 = det3d(c0a, mat[0][ia], mat[0][ib]);
@@ -474,7 +446,7 @@ __device__ __forceinline__ bool box3_proj_bound(const Box3 &a, const Box3 &b, fl
 }
 
 // Symmetric by construction (canonical argument order), like rrect_iou.
-PP_B3_FN float box3_iou(const Box3 &a, const Box3 &b, float *vol_out)
+PP_B3_ENTRY float box3_iou(const Box3 &a, const Box3 &b, float *vol_out)
 {
     bool swap = false;
 #pragma unroll
@@ -486,6 +458,78 @@ PP_B3_FN float box3_iou(const Box3 &a, const Box3 &b, float *vol_out)
     if (vol_out) *vol_out = (float)v;
     const double u = vp + vq - v;
     return u > 0.0 ? (float)(v / u) : 0.f;
+}
+
+// ---- rotated BEV rectangles: intersection area, float64, branch-free (r2) -----------------------------------------
+// The 2-D case of the face-area routine above: in a's own (u, v) in [0,1]^2 parameters the part of a inside b is the unit
+// square cut by two strips (b's two axes), so area(a n b) = area(a) * that area.  Strips are closed and widened by eps
+// so that an edge of a lying on an edge of b is counted by the square's edge only.
+PP_B3_FN double strips2_area(const double c0[2], const double cu[2], const double cv[2], const double lo[2], const double hi[2])
+{
+    double rcu[2], rcv[2], rnn[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        rcu[k] = b3_rcp(cu[k]);
+        rcv[k] = b3_rcp(cv[k]);
+        const double nn = cu[k] * cu[k] + cv[k] * cv[k];
+        const double r = b3_rcp(nn);
+        rnn[k] = b3_tiny(nn) ? 0.0 : r;
+    }
+    const double rx = b3_rcp(cu[0] * cv[1] - cv[0] * cu[1]);
+    double tmin = 0.0, tmax = 1.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) b3_cut(tmin, tmax, c0[k] + cu[k], rcv[k], rcv[k] >= 0.0, lo[k], hi[k]);
+    double area = tmax > tmin ? tmax - tmin : 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int j = 1 - k;
+        const double du = cv[k], dv = -cu[k];
+        const double r_u = rcv[k], r_v = -rcu[k], r_j = k ? rx : -rx;     // 1 / (cu[j] du + cv[j] dv)
+        const bool p_u = r_u >= 0.0, p_v = r_v >= 0.0, p_j = r_j >= 0.0;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const double sc = ((side ? hi[k] : lo[k]) - c0[k]) * rnn[k];
+            const double pu = cu[k] * sc, pv = cv[k] * sc;
+            double t0 = -1e300, t1 = 1e300;
+            b3_cut(t0, t1, pu, r_u, p_u, 0.0, 1.0);
+            b3_cut(t0, t1, pv, r_v, p_v, 0.0, 1.0);
+            b3_cut(t0, t1, c0[j] + cu[j] * pu + cv[j] * pv, r_j, p_j, lo[j], hi[j]);
+            const double c = 0.5 * (2.0 * pu + (t0 + t1) * du) * ((t1 - t0) * dv);
+            const bool ok = t1 > t0 && rnn[k] != 0.0;
+            area += ok ? (side ? -c : c) : 0.0;
+        }
+    }
+    return area;
+}
+
+PP_B3_FN double rrect_inter_area(const RRect &a, const RRect &b)
+{
+    const double hxa = a.hx, hya = a.hy, hxb = b.hx, hyb = b.hy;
+    if (!(hxa > 0.0) || !(hya > 0.0) || !(hxb > 0.0) || !(hyb > 0.0)) return 0.0;
+    const double ac = a.c, as = a.s, bc = b.c, bs = b.s;
+    const double dx = (double)a.cx - (double)b.cx, dy = (double)a.cy - (double)b.cy;
+    // a's axes in b's frame: ua = (cc, cs), va = (-cs, cc)
+    const double cc = ac * bc + as * bs, cs = as * bc - ac * bs;
+    const double ix = 0.5 / hxb, iy = 0.5 / hyb;
+    const double ox = dx * bc + dy * bs, oy = dy * bc - dx * bs;       // a's centre in b's frame
+    double c0[2], cu[2], cv[2];
+    cu[0] = 2.0 * hxa * cc * ix;  cv[0] = -2.0 * hya * cs * ix;  c0[0] = (ox - hxa * cc + hya * cs) * ix + 0.5;
+    cu[1] = 2.0 * hxa * cs * iy;  cv[1] = 2.0 * hya * cc * iy;   c0[1] = (oy - hxa * cs - hya * cc) * iy + 0.5;
+    const double lo[2] = {-B3_EPS, -B3_EPS}, hi[2] = {1.0 + B3_EPS, 1.0 + B3_EPS};
+    const double area = strips2_area(c0, cu, cv, lo, hi);
+    return 4.0 * hxa * hya * fmin(fmax(area, 0.0), 1.0);
+}
+
+// Symmetric by construction: the pair is put into a canonical order first, so iou(a,b) == iou(b,a) bit for bit (the
+// NMS decision must not depend on which box is "selected" and which "remaining").
+PP_B3_ENTRY float rrect_iou(const RRect &a, const RRect &b)
+{
+    const bool swap = (a.cx > b.cx) || (a.cx == b.cx && (a.cy > b.cy || (a.cy == b.cy && (a.hx > b.hx ||
+                      (a.hx == b.hx && (a.hy > b.hy || (a.hy == b.hy && a.s > b.s)))))));
+    const RRect &p = swap ? b : a, &q = swap ? a : b;
+    const double inter = rrect_inter_area(p, q);
+    const double uni = 4.0 * (double)p.hx * (double)p.hy + 4.0 * (double)q.hx * (double)q.hy - inter;
+    return (float)(inter / fmax(uni, 1e-6));
 }
 
 }  // namespace pp

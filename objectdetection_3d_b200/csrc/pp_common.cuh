@@ -1,6 +1,5 @@
 // Shared helpers for libpp_b200 (sm_100a only).
 #pragma once
-#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -94,13 +93,6 @@ template <typename... P> __device__ __forceinline__ void pdl_enter(P &...ptrs)
     (pdl_launder(ptrs), ...);
 }
 
-// development switch: PP_NO_PDL=1 in the environment launches everything the plain way
-inline bool pdl_allowed()
-{
-    static const bool on = [] { const char *e = getenv("PP_NO_PDL"); return !(e && e[0] == '1'); }();
-    return on;
-}
-
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args... args)
@@ -114,7 +106,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_allowed() ? 1 : 0;
+    cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -260,12 +260,18 @@ struct SortWs {
     int tiles;
 };
 
-constexpr int SORT_ITEMS = 8;
+// Keys per thread of a digit pass.  Small inputs (the NMS and top-k sizes) are latency-bound -- 20 k keys are 10 tiles
+// of 2048, each thread ranking 8 keys one after the other -- so they get 4x as many tiles of a quarter the size; the
+// look-back of <= SORT_DIRECT_TILES tiles is one round of independent loads either way.
+constexpr int SORT_ITEMS = 8, SORT_ITEMS_SMALL = 2;
+constexpr int64_t SORT_SMALL_N = 32768;
+constexpr int SORT_DIRECT_TILES = 64;
+inline int sort_items(int64_t n) { return n <= SORT_SMALL_N ? SORT_ITEMS_SMALL : SORT_ITEMS; }
 
 SortWs carve(void *ws, int64_t n, size_t *total)
 {
     SortWs s;
-    s.tiles = (int)ceil_div(n > 0 ? n : 1, (int64_t)SORT_THREADS * SORT_ITEMS);
+    s.tiles = (int)ceil_div(n > 0 ? n : 1, (int64_t)SORT_THREADS * sort_items(n));
     Arena a(ws, (size_t)-1);
     s.hist = a.take<uint32_t>(NPASS * RADIX);
     s.tickets = a.take<uint32_t>(64);
@@ -313,16 +319,22 @@ int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *k
         PP_CUDA_TRY(cudaMemsetAsync(ws, 0, s.zero_bytes, st));
         prof_mark("memset");
     }
-    int hist_blocks = (int)(ceil_div(n, SORT_THREADS * 16) < 148 * 4 ? ceil_div(n, SORT_THREADS * 16) : 148 * 4);
+    const int64_t per_block = n <= SORT_SMALL_N ? SORT_THREADS * 4 : SORT_THREADS * 16;
+    int hist_blocks = (int)(ceil_div(n, per_block) < 148 * 4 ? ceil_div(n, per_block) : 148 * 4);
     sort_hist_kernel<<<hist_blocks, SORT_THREADS, 0, st>>>(keys_in, n, s.hist);
     if (int rc = check_launch("sort_hist_kernel")) return rc;
     const uint32_t *kin = keys_in, *vin = vals_in;
     for (int p = 0; p < NPASS; ++p) {
         uint32_t *kout = (p & 1) ? keys_out : s.keys_tmp;
         uint32_t *vout = (p & 1) ? vals_out : s.vals_tmp;
-        sort_pass_kernel<SORT_ITEMS><<<s.tiles, SORT_THREADS, 0, st>>>(
-            kin, vin, kout, vout, n, p, s.hist + p * RADIX, s.status + (size_t)p * s.tiles * RADIX, s.tickets + p,
-            s.tiles <= 32);
+        if (sort_items(n) == SORT_ITEMS_SMALL)
+            sort_pass_kernel<SORT_ITEMS_SMALL><<<s.tiles, SORT_THREADS, 0, st>>>(
+                kin, vin, kout, vout, n, p, s.hist + p * RADIX, s.status + (size_t)p * s.tiles * RADIX, s.tickets + p,
+                s.tiles <= SORT_DIRECT_TILES);
+        else
+            sort_pass_kernel<SORT_ITEMS><<<s.tiles, SORT_THREADS, 0, st>>>(
+                kin, vin, kout, vout, n, p, s.hist + p * RADIX, s.status + (size_t)p * s.tiles * RADIX, s.tickets + p,
+                s.tiles <= SORT_DIRECT_TILES);
         if (int rc = check_launch("sort_pass_kernel")) return rc;
         kin = kout;
         vin = vout;

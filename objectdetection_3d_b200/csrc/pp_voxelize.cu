@@ -393,7 +393,9 @@ __global__ void __launch_bounds__(CELLS_THREADS) vox_cells_kernel(const VoxParam
     }
     uint32_t total = 0, m = 0, n0 = 0;
     int sat = NCH - 1;
-    {
+    u64 mine = 0, incl = 0;
+    // (nine warps in ten hold only empty slots on the benchmark tile: they skip the counting and the warp scan)
+    if (__any_sync(0xFFFFFFFFu, (c[0] | c[1] | c[2] | c[3] | c[4] | c[5] | c[6] | c[7]) != 0u)) {
         bool found = false;
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
@@ -402,16 +404,16 @@ __global__ void __launch_bounds__(CELLS_THREADS) vox_cells_kernel(const VoxParam
             if (!found && total >= (uint32_t)prm.P) { found = true; sat = k; m = total; }
         }
         if (!found) m = total;
+        // exclusive prefix over the CTA of (m, occupied) packed in one 64-bit word (m < 2^31, at most 1024 cells per CTA)
+        mine = ((u64)m << 11) | (total > 0 ? 1ull : 0ull);
+        incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned lo = __shfl_up_sync(0xFFFFFFFFu, (unsigned)incl, o), hi = __shfl_up_sync(0xFFFFFFFFu, (unsigned)(incl >> 32), o);
+            if (lane >= o) incl += ((u64)hi << 32) | lo;
+        }
     }
     const bool occ = total > 0;
-    // exclusive prefix over the CTA of (m, occupied) packed in one 64-bit word (m < 2^31, at most 1024 cells per CTA)
-    const u64 mine = ((u64)m << 11) | (occ ? 1ull : 0ull);
-    u64 incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned lo = __shfl_up_sync(0xFFFFFFFFu, (unsigned)incl, o), hi = __shfl_up_sync(0xFFFFFFFFu, (unsigned)(incl >> 32), o);
-        if (lane >= o) incl += ((u64)hi << 32) | lo;
-    }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     if (warp == 0) {

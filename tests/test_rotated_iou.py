@@ -64,7 +64,7 @@ def test_cuda_rotated_iou_and_nms(oracle):
     a, b = _boxes(700, 5, 20.0), _boxes(900, 6, 20.0)
     got = ops_torch.bbox_iou_rotated_bev(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
     ref = oracle.bbox_iou_rotated_bev(a, b)
-    assert np.abs(got - ref).max() < 2e-5          # T1: fp32 clipping vs the float64 oracle
+    assert np.abs(got - ref).max() < 2e-6          # T1: float64 evaluation (fp32 sin, cos and output) vs the float64 oracle
     assert ops_torch.bbox_iou_rotated_bev(torch.from_numpy(a[:0]).cuda(), torch.from_numpy(b).cuda()).shape == (0, 900)
     # rotated NMS: identical to a CPU greedy loop driven by the GPU's own IoU matrix
     for n, extent in ((3000, 25.0), (20000, 40.0)):
