@@ -669,22 +669,31 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
         __syncthreads();
         const int kn = min(NMS_THREADS, k1 - k0);
         if (valid && !dead) {
-            for (int j = part; j < kn; j += FLT_SPLIT) {
-                const float4 q = s_k[j];
-                // empty intersection -> iou == 0 exactly; otherwise bbox_iou2D with (remaining, selected) = (box, kept)
-                const bool apart = !(fminf(box.z, q.z) > fmaxf(box.x, q.x) && fminf(box.w, q.w) > fmaxf(box.y, q.y));
-                bool hit;
-                if (apart) hit = zero_hits;
-                else if (MODE != PP_NMS_AABB2D) hit = G::exceeds(gbox, G::load(s_k0, s_k1, s_k2, j), thr);
-                else hit = rect_iou(box, q, 0, 1e-6f) > thr;
-                if (hit) { dead = true; break; }
+            // four kept boxes per step (independent loads and compares: the loop is latency-bound at two CTAs per SM)
+            for (int j0 = part; j0 < kn && !dead; j0 += 4 * FLT_SPLIT) {
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u * FLT_SPLIT;
+                    if (j < kn) {
+                        const float4 q = s_k[j];
+                        // empty intersection -> iou == 0 exactly; otherwise bbox_iou2D with (remaining, selected) = (box, kept)
+                        const bool apart = !(fminf(box.z, q.z) > fmaxf(box.x, q.x) && fminf(box.w, q.w) > fmaxf(box.y, q.y));
+                        bool hit;
+                        if (apart) hit = zero_hits;
+                        else if (MODE != PP_NMS_AABB2D) hit = G::exceeds(gbox, G::load(s_k0, s_k1, s_k2, j), thr);
+                        else hit = rect_iou(box, q, 0, 1e-6f) > thr;
+                        any |= hit;
+                    }
+                }
+                dead = any;
             }
         }
         __syncthreads();
     }
     if (dead) s_dead[bi] = 1;
     __syncthreads();
-    // ordered compaction: block scan of the survivor flags + decoupled look-back over the (ticket-ordered) tiles
+    // ordered compaction: block scan of the survivor flags + exclusive prefix over the (ticket-ordered) tiles
     const bool alive = tid < FLT_BOXES && (n1 + (int)tile * FLT_BOXES + tid) < n && !s_dead[tid];
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
     if (lane == 0) s_warp[warp] = __popc(bal);
@@ -696,22 +705,25 @@ nms_filter_kernel(const float4 *__restrict__ srect, const uint32_t *__restrict__
         if (w < warp) wbase += c;
         total += c;
     }
+    // exclusive prefix over the (ticket-ordered) tiles: the tile publishes its count, then all its threads read the counts
+    // of ALL predecessors with independent loads (a few hundred tiles: one L2 round trip and a block reduction instead of
+    // a look-back chain of dependent loads, which was most of this kernel's time)
+    if (tid == 0) atomicExch(status + tile, FLT_AGG | total);
+    uint32_t before = 0;
+    for (uint32_t t = tid; t < tile; t += NMS_THREADS) {
+        uint32_t v;
+        do { v = *((volatile uint32_t *)(status + t)); } while ((v & FLT_MASK) == 0);
+        before += v & ~FLT_MASK;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
+    __syncthreads();                      // (s_warp is read above)
+    if (lane == 0) s_warp[warp] = before;
+    __syncthreads();
     if (tid == 0) {
         uint32_t excl = 0;
-        if (tile == 0) {
-            atomicExch(status, FLT_PREFIX | total);
-        } else {
-            atomicExch(status + tile, FLT_AGG | total);
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                const uint32_t v = *((volatile uint32_t *)(status + t));
-                if ((v & FLT_MASK) == 0) continue;
-                excl += v & ~FLT_MASK;
-                if ((v & FLT_MASK) == FLT_PREFIX) break;
-                --t;
-            }
-            atomicExch(status + tile, FLT_PREFIX | (excl + total));
-        }
+#pragma unroll
+        for (int w = 0; w < NMS_THREADS / 32; ++w) excl += s_warp[w];
         s_excl = excl;
         if ((int)tile == num_tiles - 1) sc[SC_N2] = (int32_t)(excl + total);
     }
@@ -828,7 +840,7 @@ nms_filter_clip_kernel(const float4 *__restrict__ srect, const uint32_t *__restr
         __syncthreads();
         if (k0 >= k1) break;
     }
-    // ordered compaction: block scan of the survivor flags + decoupled look-back over the (ticket-ordered) tiles
+    // ordered compaction: block scan of the survivor flags + exclusive prefix over the (ticket-ordered) tiles
     const bool alive = tid < FLT_BOXES && !s_dead[tid];
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
     if (lane == 0) s_warp[warp] = __popc(bal);
@@ -840,22 +852,25 @@ nms_filter_clip_kernel(const float4 *__restrict__ srect, const uint32_t *__restr
         if (w < warp) wbase += c;
         total += c;
     }
+    // exclusive prefix over the (ticket-ordered) tiles: the tile publishes its count, then all its threads read the counts
+    // of ALL predecessors with independent loads (a few hundred tiles: one L2 round trip and a block reduction instead of
+    // a look-back chain of dependent loads, which was most of this kernel's time)
+    if (tid == 0) atomicExch(status + tile, FLT_AGG | total);
+    uint32_t before = 0;
+    for (uint32_t t = tid; t < tile; t += NMS_THREADS) {
+        uint32_t v;
+        do { v = *((volatile uint32_t *)(status + t)); } while ((v & FLT_MASK) == 0);
+        before += v & ~FLT_MASK;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
+    __syncthreads();                      // (s_warp is read above)
+    if (lane == 0) s_warp[warp] = before;
+    __syncthreads();
     if (tid == 0) {
         uint32_t excl = 0;
-        if (tile == 0) {
-            atomicExch(status, FLT_PREFIX | total);
-        } else {
-            atomicExch(status + tile, FLT_AGG | total);
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                const uint32_t v = *((volatile uint32_t *)(status + t));
-                if ((v & FLT_MASK) == 0) continue;
-                excl += v & ~FLT_MASK;
-                if ((v & FLT_MASK) == FLT_PREFIX) break;
-                --t;
-            }
-            atomicExch(status + tile, FLT_PREFIX | (excl + total));
-        }
+#pragma unroll
+        for (int w = 0; w < NMS_THREADS / 32; ++w) excl += s_warp[w];
         s_excl = excl;
         if ((int)tile == num_tiles - 1) sc[SC_N2] = (int32_t)(excl + total);
     }
