@@ -608,7 +608,7 @@ def detail_legs(args, torch, dist, dev, world, rank, pipe, nms, slots, d_pts, d_
         "nms_20k": {"us": t_nms, "target_us": 1000.0, "kept": keep_n,
                     "pair_test": "xy rectangle of the rotated box (the reference's nms_dim == 2)"},
         "nms_20k_rotated_bev": {"us": t_rot, "target_us": 1000.0, "kept": kept_rot,
-                                "pair_test": "rotated BEV polygon clipping (north-star extension)"},
+                                "pair_test": "rotated BEV footprint IoU (north-star extension)"},
         "nms_20k_box3d": {"us": t_b3d, "kept": kept_b3d,
                           "pair_test": "oriented 3-D box IoU (the reference's nms_dim == 3, config.yaml:6)"}}
 
