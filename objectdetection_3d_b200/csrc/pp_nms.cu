@@ -69,13 +69,16 @@ template <> struct PairGeom<PP_NMS_BOX3D> {
     static __device__ __forceinline__ bool exceeds(const T &a, const T &b, float thr) { return maybe(a, b, thr) && exact(a, b, thr); }
 };
 
-__global__ void __launch_bounds__(NMS_THREADS)
+constexpr int PREP_THREADS = 1024;          // large CTAs: each adds its keys' digit histograms to the sort's with few atomics
+__global__ void __launch_bounds__(PREP_THREADS)
 nms_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ scores, int64_t stride, int64_t N,
                    float score_thr, float4 *__restrict__ rect, uint32_t *__restrict__ keys, int32_t *__restrict__ n_cand,
-                   int mode, const Aux aux)
+                   int mode, const Aux aux, uint32_t *__restrict__ sort_hist_out)
 {
-    int64_t i = (int64_t)blockIdx.x * NMS_THREADS + threadIdx.x;
+    __shared__ uint32_t s_hist[1024];
+    int64_t i = (int64_t)blockIdx.x * PREP_THREADS + threadIdx.x;
     bool cand = false;
+    uint32_t key = 0xFFFFFFFFu;
     if (i < N) {
         float b[9];
 #pragma unroll
@@ -98,10 +101,12 @@ nms_prepare_kernel(const float *__restrict__ boxes, const float *__restrict__ sc
         }
         float s = scores[i * stride];
         cand = s > score_thr;
-        keys[i] = cand ? ~ordered_bits(s) : 0xFFFFFFFFu;
+        key = cand ? ~ordered_bits(s) : 0xFFFFFFFFu;
+        keys[i] = key;
     }
     unsigned m = __ballot_sync(0xFFFFFFFFu, cand);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_cand, __popc(m));
+    if (sort_hist_out) sort_hist_add(s_hist, sort_hist_out, key, i < N);      // (the sort orders all N keys)
 }
 
 __global__ void __launch_bounds__(NMS_THREADS)
@@ -1006,10 +1011,10 @@ extern "C" int pp_nms_mode(const float *boxes9, const float *scores, int64_t sco
     // per device and context, cheap: set on every call (a process may drive several GPUs, from several threads)
     PP_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_MAX));
     const unsigned nb = (unsigned)ceil_div(N, NMS_THREADS);
-    nms_prepare_kernel<<<nb, NMS_THREADS, 0, st>>>(boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.sc + SC_N,
-                                                   iou_mode, w.aux);
+    nms_prepare_kernel<<<(unsigned)ceil_div(N, PREP_THREADS), PREP_THREADS, 0, st>>>(
+        boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.sc + SC_N, iou_mode, w.aux, sort_hist(w.sort_ws, N));
     if (int rc = check_launch("nms_prepare_kernel")) return rc;
-    if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st, true)) return rc;
+    if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st, true, true)) return rc;
     nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.sc, w.srect, NMS_LEVEL1, w.aux, w.saux);
     if (int rc = check_launch("nms_gather_kernel")) return rc;
     // level 1: greedy NMS of the NMS_LEVEL1 best-scored candidates

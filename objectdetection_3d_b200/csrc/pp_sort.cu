@@ -292,6 +292,13 @@ size_t sort_workspace_bytes(int64_t n)
     return total;
 }
 
+uint32_t *sort_hist(void *ws, int64_t n)
+{
+    if (n <= SMALL_MAX) return nullptr;
+    size_t total;
+    return carve(ws, n, &total).hist;
+}
+
 size_t sort_zero_bytes(int64_t n)
 {
     size_t total;
@@ -299,7 +306,7 @@ size_t sort_zero_bytes(int64_t n)
 }
 
 int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
-                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st, bool ws_zeroed)
+                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st, bool ws_zeroed, bool have_hist)
 {
     if (n <= 0) return PP_OK;
     PP_REQUIRE(n < (1ll << 30), "n must be < 2^30");
@@ -319,10 +326,12 @@ int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *k
         PP_CUDA_TRY(cudaMemsetAsync(ws, 0, s.zero_bytes, st));
         prof_mark("memset");
     }
-    const int64_t per_block = n <= SORT_SMALL_N ? SORT_THREADS * 4 : SORT_THREADS * 16;
-    int hist_blocks = (int)(ceil_div(n, per_block) < 148 * 4 ? ceil_div(n, per_block) : 148 * 4);
-    sort_hist_kernel<<<hist_blocks, SORT_THREADS, 0, st>>>(keys_in, n, s.hist);
-    if (int rc = check_launch("sort_hist_kernel")) return rc;
+    if (!(have_hist && ws_zeroed)) {
+        const int64_t per_block = n <= SORT_SMALL_N ? SORT_THREADS * 4 : SORT_THREADS * 16;
+        int hist_blocks = (int)(ceil_div(n, per_block) < 148 * 4 ? ceil_div(n, per_block) : 148 * 4);
+        sort_hist_kernel<<<hist_blocks, SORT_THREADS, 0, st>>>(keys_in, n, s.hist);
+        if (int rc = check_launch("sort_hist_kernel")) return rc;
+    }
     const uint32_t *kin = keys_in, *vin = vals_in;
     for (int p = 0; p < NPASS; ++p) {
         uint32_t *kout = (p & 1) ? keys_out : s.keys_tmp;

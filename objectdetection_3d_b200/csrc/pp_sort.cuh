@@ -9,6 +9,26 @@ size_t sort_workspace_bytes(int64_t n);
 size_t sort_zero_bytes(int64_t n);
 // vals_in == nullptr means "iota": the value of element i is i.  ws_zeroed: the caller has already zeroed the first
 // sort_zero_bytes(n) bytes of ws on this stream (as part of a memset of its own), so the sort issues none.
+// have_hist (needs ws_zeroed): the kernel that produced keys_in has also accumulated the four 8-bit digit histograms of
+// ALL n keys into sort_hist(ws, n) (sort_hist_add below), so the sort skips its histogram launch; sort_hist returns
+// nullptr for sizes the one-CTA path sorts (no histogram needed).
 int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
-                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st, bool ws_zeroed = false);
+                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st, bool ws_zeroed = false, bool have_hist = false);
+uint32_t *sort_hist(void *ws, int64_t n);
+
+#ifdef __CUDACC__
+// block-wide: every thread passes its key (valid = false for none); sh is 1024 words of shared memory
+__device__ __forceinline__ void sort_hist_add(uint32_t *sh, uint32_t *hist, uint32_t key, bool valid)
+{
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    if (valid) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) atomicAdd(&sh[p * 256 + ((key >> (8 * p)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+#endif
 }  // namespace pp
