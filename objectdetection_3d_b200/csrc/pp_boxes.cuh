@@ -143,6 +143,8 @@ __device__ __forceinline__ RRect rrect_pack(const float4 lo, const float2 hi)
 struct Box3 {
     float o[3], e[3][3];
 };
+// (tests/host/iou_host.cu defines PP_B3_FN as `__host__ __device__ inline` to check this arithmetic against the oracle
+// on a machine without a GPU; the library itself is only ever built for the device)
 #ifndef PP_B3_FN
 #define PP_B3_FN __device__ __forceinline__
 // The two IoU entry points are NOT inlined: every kernel of a translation unit then runs the same instructions, so the
