@@ -1014,9 +1014,23 @@ extern "C" int pp_nms_mode(const float *boxes9, const float *scores, int64_t sco
     nms_prepare_kernel<<<(unsigned)ceil_div(N, PREP_THREADS), PREP_THREADS, 0, st>>>(
         boxes9, scores, score_stride, N, score_thr, w.rect, w.keys, w.sc + SC_N, iou_mode, w.aux, sort_hist(w.sort_ws, N));
     if (int rc = check_launch("nms_prepare_kernel")) return rc;
-    if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st, true, true)) return rc;
-    nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.sc, w.srect, NMS_LEVEL1, w.aux, w.saux);
-    if (int rc = check_launch("nms_gather_kernel")) return rc;
+    // the sort's last pass moves the rectangles (and the geometry of the clipped modes) with their keys and sets the size
+    // of level 1; sizes that the one-CTA sort handles use the gather kernel
+    SortTail tail = {};
+    tail.in[0] = w.rect; tail.out[0] = w.srect; tail.arrays = 1;
+    const float4 *ain[3] = {w.aux.a0, w.aux.a1, w.aux.a2};
+    float4 *aout[3] = {w.saux.a0, w.saux.a1, w.saux.a2};
+    for (int k = 0; k < 3; ++k)
+        if (ain[k]) { tail.in[tail.arrays] = ain[k]; tail.out[tail.arrays] = aout[k]; ++tail.arrays; }
+    tail.count_in = w.sc + SC_N; tail.count_out = w.sc + SC_N1; tail.count_cap = NMS_LEVEL1;
+    const bool fused_gather = sort_runs_tail(N);
+    if (int rc = sort_pairs_u32(w.keys, nullptr, w.keys_sorted, w.order, N, w.sort_ws, w.sort_ws_bytes, st, true, true,
+                                fused_gather ? &tail : nullptr))
+        return rc;
+    if (!fused_gather) {
+        nms_gather_kernel<<<nb, NMS_THREADS, 0, st>>>(w.rect, w.order, w.sc, w.srect, NMS_LEVEL1, w.aux, w.saux);
+        if (int rc = check_launch("nms_gather_kernel")) return rc;
+    }
     // level 1: greedy NMS of the NMS_LEVEL1 best-scored candidates
     const int64_t l1 = N < NMS_LEVEL1 ? N : NMS_LEVEL1;
     if (int rc = launch_level(w.srect, w.sc + SC_N1, l1, iou_thr, w.nw1, w.mask1, w.band1, w.order, keep, nullptr,

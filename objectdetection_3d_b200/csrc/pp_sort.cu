@@ -40,12 +40,12 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const uint32_t 
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-template <int ITEMS>
+template <int ITEMS, bool TAIL>
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int pass,
                  const uint32_t *__restrict__ hist /* this pass: [256] */, uint32_t *status /* [tiles][256] */,
-                 uint32_t *ticket, bool direct)
+                 uint32_t *ticket, bool direct, const SortTail tail)
 {
     constexpr int TILE = SORT_THREADS * ITEMS;
     __shared__ uint32_t warp_hist[SORT_WARPS][RADIX + 1];
@@ -146,8 +146,18 @@ sort_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restric
             uint32_t d = (key[r] >> shift) & (RADIX - 1);
             uint32_t dst = digit_off[d] + warp_hist[warp][d] + rank[r];
             keys_out[dst] = key[r];
-            vals_out[dst] = vals_in ? vals_in[idx] : (uint32_t)idx;
+            const uint32_t val = vals_in ? vals_in[idx] : (uint32_t)idx;
+            vals_out[dst] = val;
+            if (TAIL) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                    if (a < tail.arrays) tail.out[a][dst] = tail.in[a][val];
+            }
         }
+    }
+    if (TAIL && tile == 0 && tid == 0 && tail.count_out) {
+        const int32_t c = *tail.count_in;
+        *tail.count_out = c < tail.count_cap ? c : tail.count_cap;
     }
 }
 
@@ -292,6 +302,8 @@ size_t sort_workspace_bytes(int64_t n)
     return total;
 }
 
+bool sort_runs_tail(int64_t n) { return n > SMALL_MAX; }
+
 uint32_t *sort_hist(void *ws, int64_t n)
 {
     if (n <= SMALL_MAX) return nullptr;
@@ -306,7 +318,8 @@ size_t sort_zero_bytes(int64_t n)
 }
 
 int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
-                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st, bool ws_zeroed, bool have_hist)
+                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st, bool ws_zeroed, bool have_hist,
+                   const SortTail *tail)
 {
     if (n <= 0) return PP_OK;
     PP_REQUIRE(n < (1ll << 30), "n must be < 2^30");
@@ -336,14 +349,15 @@ int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *k
     for (int p = 0; p < NPASS; ++p) {
         uint32_t *kout = (p & 1) ? keys_out : s.keys_tmp;
         uint32_t *vout = (p & 1) ? vals_out : s.vals_tmp;
-        if (sort_items(n) == SORT_ITEMS_SMALL)
-            sort_pass_kernel<SORT_ITEMS_SMALL><<<s.tiles, SORT_THREADS, 0, st>>>(
-                kin, vin, kout, vout, n, p, s.hist + p * RADIX, s.status + (size_t)p * s.tiles * RADIX, s.tickets + p,
-                s.tiles <= SORT_DIRECT_TILES);
-        else
-            sort_pass_kernel<SORT_ITEMS><<<s.tiles, SORT_THREADS, 0, st>>>(
-                kin, vin, kout, vout, n, p, s.hist + p * RADIX, s.status + (size_t)p * s.tiles * RADIX, s.tickets + p,
-                s.tiles <= SORT_DIRECT_TILES);
+        const bool with_tail = tail && p == NPASS - 1;
+        const SortTail t = with_tail ? *tail : SortTail();
+#define PP_PASS(IT, TL)                                                                                               \
+    sort_pass_kernel<IT, TL><<<s.tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, p, s.hist + p * RADIX,        \
+                                                               s.status + (size_t)p * s.tiles * RADIX, s.tickets + p, \
+                                                               s.tiles <= SORT_DIRECT_TILES, t)
+        if (sort_items(n) == SORT_ITEMS_SMALL) { if (with_tail) PP_PASS(SORT_ITEMS_SMALL, true); else PP_PASS(SORT_ITEMS_SMALL, false); }
+        else { if (with_tail) PP_PASS(SORT_ITEMS, true); else PP_PASS(SORT_ITEMS, false); }
+#undef PP_PASS
         if (int rc = check_launch("sort_pass_kernel")) return rc;
         kin = kout;
         vin = vout;

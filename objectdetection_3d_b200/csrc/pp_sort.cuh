@@ -12,8 +12,21 @@ size_t sort_zero_bytes(int64_t n);
 // have_hist (needs ws_zeroed): the kernel that produced keys_in has also accumulated the four 8-bit digit histograms of
 // ALL n keys into sort_hist(ws, n) (sort_hist_add below), so the sort skips its histogram launch; sort_hist returns
 // nullptr for sizes the one-CTA path sorts (no histogram needed).
+// tail (multi-pass sizes only, see sort_runs_tail): work the LAST digit pass does on the side, saving the caller a launch:
+// out[a][rank] = in[a][value] for every element and each of `arrays` float4 arrays (the payload moves with its key), and
+// *count_out = min(*count_in, count_cap).
+struct SortTail {
+    const float4 *in[4];
+    float4 *out[4];
+    int arrays;
+    const int32_t *count_in;
+    int32_t *count_out;
+    int count_cap;
+};
+bool sort_runs_tail(int64_t n);
 int sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
-                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st, bool ws_zeroed = false, bool have_hist = false);
+                   int64_t n, void *ws, size_t ws_bytes, cudaStream_t st, bool ws_zeroed = false, bool have_hist = false,
+                   const SortTail *tail = nullptr);
 uint32_t *sort_hist(void *ws, int64_t n);
 
 #ifdef __CUDACC__
