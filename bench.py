@@ -575,7 +575,7 @@ def detail_legs(args, torch, dist, dev, world, rank, pipe, nms, slots, d_pts, d_
         ach = b / (k["avg_us"] * 1e-6) / 1e9
         # the library's profiler names the PFN-fused gather separately; in the ncu table it is a template instance
         alias = {"vox_gather_pfn_kernel": "vox_gather_kernel<unsigned long long, 1, 1>",
-                 "scatter_canvas_kernel": "scatter_canvas_wave_kernel", "sort_pass_kernel": "sort_pass_kernel<8>",
+                 "scatter_canvas_kernel": "scatter_canvas_wave_kernel", "sort_pass_kernel": "sort_pass_kernel<2, 0>",
                  "nms_mask_kernel": "nms_mask_kernel<1, 0>", "nms_filter_kernel": "nms_filter_kernel<0>"}
         tab = ncu.get("kernels", {})
         t = tab.get(alias.get(name, name)) or tab.get(name, {})
