@@ -1,11 +1,18 @@
-// One class of multiclass_nms (model/utils.py:376-424, nms_dim == 2):
-//   prepare : AABB of the rotated box (ops/ops_torch.py:13-114), score filter (strict >, :381), sort key
-//   sort    : descending score, stable (ties: lower index first)  [pp_sort.cu]
-//   mask    : 64x64 tiles of the upper triangle, bit j of mask[i][cb] = iou(box_j, box_i) > thr (strict, :413)
-//   sweep   : one CTA walks the 64-box blocks in order; a warp resolves each diagonal block with a
-//             64-step register chain, then all threads OR the kept rows into the running removed mask.
-// The IoU is evaluated exactly like bbox_iou2D (pp_boxes.cuh::rect_iou), so the keep set is identical
-// to the reference's greedy loop on the same rectangles.
+// One class of multiclass_nms (model/utils.py:376-424; nms_dim == 2 and, through the pair-test template, nms_dim == 3
+// and the rotated-BEV extension):
+//   prepare : AABB of the rotated box (ops/ops_torch.py:13-114), pair-test geometry, score filter (strict >, :381), sort
+//             key, the sort's digit histograms
+//   sort    : descending score, stable (ties: lower index first); the last pass moves the rectangles and the geometry
+//             with their keys  [pp_sort.cu]
+//   level 1 : greedy NMS of the NMS_LEVEL1 best candidates = mask + sweep
+//   filter  : drops every lower candidate the level-1 keep set suppresses, compacts the survivors in rank order
+//   level 2 : greedy NMS of the survivors = mask + sweep
+//   mask    : tiles of the upper triangle, bit j of mask[i][cb] = iou(box_j, box_i) > thr (strict, :413); the clipped
+//             pair tests are queued per tile and evaluated with full warps
+//   sweep   : one CTA; a warp decides each 64-box block's keep set with warp OR-reductions and ORs the kept rows into
+//             the next 31 words from a shared-memory band, the other warps OR them into the words beyond
+// The rectangle IoU is evaluated exactly like bbox_iou2D (pp_boxes.cuh::rect_iou), so the keep set is identical to the
+// reference's greedy loop on the same rectangles.
 #include <cuda_fp16.h>
 
 #include "pp_boxes.cuh"
