@@ -1,9 +1,12 @@
 // Stable LSD radix sort of (u32 key, u32 value) pairs: one histogram pass + 4 single-sweep digit
 // passes with decoupled look-back ("onesweep" structure, hand-written; no CUB).
 //
-// Used by the voxelizer's reflectance pre-order (ops/ops_numba.py:262) and by NMS score ordering
-// (model/utils.py:398).  Stability is what defines the documented tie rule (lower original index
-// first).  HBM-bound: 4 x (read keys+vals, write keys+vals).
+// Used by the head's top-k (model/PointPillars.py:1056-1065) and by NMS score ordering (model/utils.py:398).
+// Stability is what defines the documented tie rule (lower original index first).  HBM-bound at large n:
+// 4 x (read keys+vals, write keys+vals); latency-bound at the NMS sizes, where the caller can zero the counters with
+// a memset of its own, supply the digit histograms from the kernel that produced the keys, and have the last pass
+// move up to four float4 payload arrays with the keys (pp_sort.cuh): three launches and a memset less per NMS call.
+// <= 4096 keys: one CTA, one launch, everything in shared memory.
 #include "pp_common.cuh"
 #include "pp_sort.cuh"
 
